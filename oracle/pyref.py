@@ -1,0 +1,427 @@
+"""TEST INFRASTRUCTURE — Python big-integer restatement of the BLS12-381 arithmetic,
+encodings and Groth16 algebra used on the prover hot path.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this.
+It is the *independent* pin for the C oracle (oracle/zk_oracle.c): it shares no code with
+either the C oracle or the CUDA kernels (affine formulas + Python ints instead of
+Jacobian/Montgomery limbs), and is itself pinned by the reference's known-answer vectors
+(tests/golden/kats.json, extracted from core/pairing/src/bls12_381/{fq,fr,fq2,ec}.rs) and
+by the 4x1000-point encoding vector files (core/pairing/src/bls12_381/tests/*.dat).
+
+Reference anchors (file:line under the reference tree):
+  Fq modulus / R / R2 / INV        core/pairing/src/bls12_381/fq.rs:5-43
+  Fr modulus / R / R2 / GENERATOR  core/pairing/src/bls12_381/fr.rs:4-55
+  Fq2 = Fq[u]/(u^2+1)              core/pairing/src/bls12_381/fq2.rs:109-158
+  curve y^2 = x^3 + 4 / 4(1+u)     core/pairing/src/bls12_381/ec.rs:885-887,1567-1572
+  point codecs                     core/pairing/src/bls12_381/ec.rs:686-867,1343-1549
+  Proof codec                      core/bellman-verifier/src/lib.rs:55-110
+  Parameters grammar               SURVEY.md §3.3 (upstream bellman 0.1.0 groth16::Parameters::write)
+"""
+from __future__ import annotations
+
+import struct
+
+# ---------------------------------------------------------------------------------------
+# constants (fq.rs:5-13, fr.rs:4-10)
+Q = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+R = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+FQ_MONT_R = (1 << 384) % Q
+FR_MONT_R = (1 << 256) % R
+FR_S = 32                      # fr.rs:47
+FR_GENERATOR = 7               # fr.rs:38-44
+FR_ROOT_OF_UNITY = pow(FR_GENERATOR, (R - 1) >> FR_S, R)   # fr.rs:50-55 (Montgomery there)
+
+G1_GEN = (
+    0x17f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb,
+    0x08b3f481e3aaa0f1a09e30ed741d8ae4fcf5e095d5d00af600db18cb2c04b3edd03cc744a2888ae40caa232946c5e7e1,
+)
+G2_GEN = (
+    (0x024aa2b2f08f0a91260805272dc51051c6e47ad4fa403b02b4510b647ae3d1770bac0326a805bbefd48056c8c121bdb8,
+     0x13e02b6052719f607dacd3a088274f65596bd0d09920b61ab5da61bbdc7f5049334cf11213945d57e5ac7d055d042b7e),
+    (0x0ce5d527727d6e118cc9cdc6da2e351aadfd9baa8cbdd3a76d429a695160d12c923ac9cc3baca289e193548608b82801,
+     0x0606c4a02ea734cc32acd2b02bc28b99cb3e287e85a763af267492ab572e99ab3f370d275cec1da1aaa9075ff05f79be),
+)
+
+
+def limbs64(x: int, n: int) -> list[int]:
+    return [(x >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(n)]
+
+
+def from_limbs64(l) -> int:
+    return sum(int(v) << (64 * i) for i, v in enumerate(l))
+
+
+def fq_to_mont(x): return (x << 384) % Q
+def fq_from_mont(x): return (x * pow(1 << 384, -1, Q)) % Q
+def fr_to_mont(x): return (x << 256) % R
+def fr_from_mont(x): return (x * pow(1 << 256, -1, R)) % R
+
+
+# ---------------------------------------------------------------------------------------
+# field "classes" as plain function tables so G1/G2 share curve code
+class _Fq:
+    zero = 0
+    one = 1
+    b = 4
+    @staticmethod
+    def add(a, b): return (a + b) % Q
+    @staticmethod
+    def sub(a, b): return (a - b) % Q
+    @staticmethod
+    def mul(a, b): return (a * b) % Q
+    @staticmethod
+    def neg(a): return (-a) % Q
+    @staticmethod
+    def inv(a): return pow(a, -1, Q)
+    @staticmethod
+    def is_zero(a): return a == 0
+    @staticmethod
+    def sqrt(a):
+        # q = 3 mod 4 (fq.rs:1152-1175)
+        s = pow(a, (Q + 1) // 4, Q)
+        return s if (s * s) % Q == a else None
+    @staticmethod
+    def gt(a, b):   # canonical integer order (fq.rs:708-713)
+        return a > b
+
+
+class _Fq2:
+    zero = (0, 0)
+    one = (1, 0)
+    b = (4, 4)
+    @staticmethod
+    def add(a, b): return ((a[0] + b[0]) % Q, (a[1] + b[1]) % Q)
+    @staticmethod
+    def sub(a, b): return ((a[0] - b[0]) % Q, (a[1] - b[1]) % Q)
+    @staticmethod
+    def mul(a, b):
+        return ((a[0] * b[0] - a[1] * b[1]) % Q, (a[0] * b[1] + a[1] * b[0]) % Q)
+    @staticmethod
+    def neg(a): return ((-a[0]) % Q, (-a[1]) % Q)
+    @staticmethod
+    def inv(a):
+        n = pow(a[0] * a[0] + a[1] * a[1], -1, Q)
+        return ((a[0] * n) % Q, (-a[1] * n) % Q)
+    @staticmethod
+    def is_zero(a): return a[0] == 0 and a[1] == 0
+    @staticmethod
+    def gt(a, b):   # c1 compared first, then c0 (fq2.rs:21-30)
+        return (a[1], a[0]) > (b[1], b[0])
+    @staticmethod
+    def sqrt(a):
+        # generic: a = (x+yu)^2 ; use norm trick
+        if a == (0, 0):
+            return (0, 0)
+        a0, a1 = a
+        if a1 == 0:
+            s = _Fq.sqrt(a0)
+            if s is not None:
+                return (s, 0)
+            s = _Fq.sqrt((-a0) % Q)
+            return (0, s) if s is not None else None
+        n = _Fq.sqrt((a0 * a0 + a1 * a1) % Q)
+        if n is None:
+            return None
+        half = pow(2, -1, Q)
+        for nn in (n, (-n) % Q):
+            x2 = ((a0 + nn) * half) % Q
+            x = _Fq.sqrt(x2)
+            if x is not None and x != 0:
+                y = (a1 * pow(2 * x, -1, Q)) % Q
+                if _Fq2.mul((x, y), (x, y)) == a:
+                    return (x, y)
+        return None
+
+
+FQ, FQ2 = _Fq, _Fq2
+INF = None   # affine infinity
+
+
+# ---------------------------------------------------------------------------------------
+# affine group law (mathematical definition; the reference's Jacobian formulas
+# ec.rs:296-526 compute the same group law)
+def ec_add(F, p, q):
+    if p is INF:
+        return q
+    if q is INF:
+        return p
+    x1, y1 = p
+    x2, y2 = q
+    if x1 == x2:
+        if y1 == y2:
+            return ec_double(F, p)
+        return INF
+    lam = F.mul(F.sub(y2, y1), F.inv(F.sub(x2, x1)))
+    x3 = F.sub(F.sub(F.mul(lam, lam), x1), x2)
+    y3 = F.sub(F.mul(lam, F.sub(x1, x3)), y1)
+    return (x3, y3)
+
+
+def ec_double(F, p):
+    if p is INF:
+        return INF
+    x1, y1 = p
+    if F.is_zero(y1):
+        return INF
+    xx = F.mul(x1, x1)
+    lam = F.mul(F.add(F.add(xx, xx), xx), F.inv(F.add(y1, y1)))
+    x3 = F.sub(F.sub(F.mul(lam, lam), x1), x1)
+    y3 = F.sub(F.mul(lam, F.sub(x1, x3)), y1)
+    return (x3, y3)
+
+
+def ec_neg(F, p):
+    return INF if p is INF else (p[0], F.neg(p[1]))
+
+
+def ec_mul(F, p, k: int):
+    if k < 0:
+        return ec_mul(F, ec_neg(F, p), -k)
+    acc = INF
+    for bit in bin(k)[2:] if k else "":
+        acc = ec_double(F, acc)
+        if bit == "1":
+            acc = ec_add(F, acc, p)
+    return acc
+
+
+def ec_on_curve(F, p):
+    if p is INF:
+        return True
+    x, y = p
+    return F.mul(y, y) == F.add(F.mul(F.mul(x, x), x), F.b)
+
+
+def ec_msm(F, bases, scalars):
+    acc = INF
+    for b, s in zip(bases, scalars):
+        if s:
+            acc = ec_add(F, acc, ec_mul(F, b, s))
+    return acc
+
+
+# ---------------------------------------------------------------------------------------
+# encodings (ec.rs:686-867 G1, 1343-1549 G2)
+def _be48(x: int) -> bytes:
+    return x.to_bytes(48, "big")
+
+
+def g1_uncompressed(p) -> bytes:
+    if p is INF:
+        return bytes([0x40]) + bytes(95)
+    return _be48(p[0]) + _be48(p[1])
+
+
+def g1_compressed(p) -> bytes:
+    if p is INF:
+        return bytes([0xC0]) + bytes(47)
+    out = bytearray(_be48(p[0]))
+    if FQ.gt(p[1], FQ.neg(p[1])):
+        out[0] |= 0x20
+    out[0] |= 0x80
+    return bytes(out)
+
+
+def g2_uncompressed(p) -> bytes:
+    if p is INF:
+        return bytes([0x40]) + bytes(191)
+    (x0, x1), (y0, y1) = p
+    return _be48(x1) + _be48(x0) + _be48(y1) + _be48(y0)
+
+
+def g2_compressed(p) -> bytes:
+    if p is INF:
+        return bytes([0xC0]) + bytes(95)
+    (x0, x1), y = p
+    out = bytearray(_be48(x1) + _be48(x0))
+    if FQ2.gt(y, FQ2.neg(y)):
+        out[0] |= 0x20
+    out[0] |= 0x80
+    return bytes(out)
+
+
+def g1_from_uncompressed(b: bytes):
+    assert len(b) == 96
+    if b[0] & 0x80:
+        raise ValueError("UnexpectedCompressionMode")
+    if b[0] & 0x40:
+        if any(b[1:]) or (b[0] & 0x3F):
+            raise ValueError("UnexpectedInformation")
+        return INF
+    if b[0] & 0x20:
+        raise ValueError("UnexpectedInformation")
+    x = int.from_bytes(b[:48], "big")
+    y = int.from_bytes(b[48:], "big")
+    if x >= Q or y >= Q:
+        raise ValueError("CoordinateDecodingError")
+    return (x, y)
+
+
+def g2_from_uncompressed(b: bytes):
+    assert len(b) == 192
+    if b[0] & 0x80:
+        raise ValueError("UnexpectedCompressionMode")
+    if b[0] & 0x40:
+        if any(b[1:]) or (b[0] & 0x3F):
+            raise ValueError("UnexpectedInformation")
+        return INF
+    if b[0] & 0x20:
+        raise ValueError("UnexpectedInformation")
+    v = [int.from_bytes(b[48 * i:48 * i + 48], "big") for i in range(4)]
+    if any(c >= Q for c in v):
+        raise ValueError("CoordinateDecodingError")
+    return ((v[1], v[0]), (v[3], v[2]))
+
+
+def g1_from_compressed(b: bytes):
+    assert len(b) == 48 and b[0] & 0x80
+    if b[0] & 0x40:
+        return INF
+    greatest = bool(b[0] & 0x20)
+    x = int.from_bytes(bytes([b[0] & 0x1F]) + b[1:], "big")
+    y = FQ.sqrt((x * x * x + 4) % Q)
+    if y is None:
+        raise ValueError("NotOnCurve")
+    ny = FQ.neg(y)
+    return (x, y if (y < ny) ^ greatest else ny)   # ec.rs:102-123
+
+
+def g2_from_compressed(b: bytes):
+    assert len(b) == 96 and b[0] & 0x80
+    if b[0] & 0x40:
+        return INF
+    greatest = bool(b[0] & 0x20)
+    x1 = int.from_bytes(bytes([b[0] & 0x1F]) + b[1:48], "big")
+    x0 = int.from_bytes(b[48:], "big")
+    x = (x0, x1)
+    y = FQ2.sqrt(FQ2.add(FQ2.mul(FQ2.mul(x, x), x), FQ2.b))
+    if y is None:
+        raise ValueError("NotOnCurve")
+    ny = FQ2.neg(y)
+    return (x, y if FQ2.gt(ny, y) ^ greatest else ny)
+
+
+def proof_bytes(a, b, c) -> bytes:
+    """core/bellman-verifier/src/lib.rs:55-65: compressed a (G1) || b (G2) || c (G1)."""
+    return g1_compressed(a) + g2_compressed(b) + g1_compressed(c)
+
+
+# ---------------------------------------------------------------------------------------
+# Parameters file (upstream bellman groth16::Parameters::{read,write})
+def params_write(vk, h, l, a, b_g1, b_g2) -> bytes:
+    """vk = dict(alpha_g1,beta_g1,beta_g2,gamma_g2,delta_g1,delta_g2,ic=[...])."""
+    out = bytearray()
+    out += g1_uncompressed(vk["alpha_g1"]) + g1_uncompressed(vk["beta_g1"])
+    out += g2_uncompressed(vk["beta_g2"]) + g2_uncompressed(vk["gamma_g2"])
+    out += g1_uncompressed(vk["delta_g1"]) + g2_uncompressed(vk["delta_g2"])
+    out += struct.pack(">I", len(vk["ic"]))
+    for p in vk["ic"]:
+        out += g1_uncompressed(p)
+    for vec, enc in ((h, g1_uncompressed), (l, g1_uncompressed), (a, g1_uncompressed),
+                     (b_g1, g1_uncompressed), (b_g2, g2_uncompressed)):
+        out += struct.pack(">I", len(vec))
+        for p in vec:
+            out += enc(p)
+    return bytes(out)
+
+
+def params_layout(buf: bytes) -> dict:
+    """Offsets/lengths only (no point decoding): returns dict name -> (offset, count)."""
+    off = 96 + 96 + 192 + 192 + 96 + 192
+    lay = {}
+    (n,) = struct.unpack_from(">I", buf, off); off += 4
+    lay["ic"] = (off, n); off += 96 * n
+    for name, sz in (("h", 96), ("l", 96), ("a", 96), ("b_g1", 96), ("b_g2", 192)):
+        (n,) = struct.unpack_from(">I", buf, off); off += 4
+        lay[name] = (off, n); off += sz * n
+    lay["end"] = (off, 0)
+    return lay
+
+
+# ---------------------------------------------------------------------------------------
+# Fr NTT (mathematical definition of upstream bellman EvaluationDomain::fft: out[k] = sum_j a[j] w^(jk))
+def omega(log_n: int) -> int:
+    return pow(FR_ROOT_OF_UNITY, 1 << (FR_S - log_n), R)
+
+
+def ntt(a, log_n, w=None):
+    n = 1 << log_n
+    assert len(a) == n
+    w = omega(log_n) if w is None else w
+    a = list(a)
+    # bit reversal
+    for i in range(n):
+        j = int(format(i, "0%db" % log_n)[::-1], 2) if log_n else 0
+        if i < j:
+            a[i], a[j] = a[j], a[i]
+    m = 1
+    for _ in range(log_n):
+        wm = pow(w, n // (2 * m), R)
+        for k in range(0, n, 2 * m):
+            t = 1
+            for j in range(m):
+                u = a[k + j]
+                v = a[k + j + m] * t % R
+                a[k + j] = (u + v) % R
+                a[k + j + m] = (u - v) % R
+                t = t * wm % R
+        m *= 2
+    return a
+
+
+def intt(a, log_n):
+    n = 1 << log_n
+    ninv = pow(n, -1, R)
+    return [x * ninv % R for x in ntt(a, log_n, pow(omega(log_n), -1, R))]
+
+
+def poly_eval(coeffs, x):
+    acc = 0
+    for c in reversed(coeffs):
+        acc = (acc * x + c) % R
+    return acc
+
+
+def h_coeffs(a_ev, b_ev, c_ev, log_n):
+    """Quotient polynomial exactly as upstream bellman create_proof:
+    ifft; coset_fft; a*b-c; divide_by_z_on_coset; icoset_fft; drop last coeff."""
+    n = 1 << log_n
+    pad = lambda v: list(v) + [0] * (n - len(v))
+    g = FR_GENERATOR
+    def coset_fft(ev):
+        co = intt(pad(ev), log_n)
+        co = [c * pow(g, i, R) % R for i, c in enumerate(co)]
+        return ntt(co, log_n)
+    A, B, C = coset_fft(a_ev), coset_fft(b_ev), coset_fft(c_ev)
+    zinv = pow((pow(g, n, R) - 1) % R, -1, R)
+    Hc = [((x * y - z) % R) * zinv % R for x, y, z in zip(A, B, C)]
+    co = intt(Hc, log_n)
+    ginv = pow(g, -1, R)
+    co = [c * pow(ginv, i, R) % R for i, c in enumerate(co)]
+    return co[: n - 1]
+
+
+# ---------------------------------------------------------------------------------------
+# deterministic RNG shared by python tests (SplitMix64)
+class SplitMix64:
+    def __init__(self, seed: int):
+        self.s = seed & 0xFFFFFFFFFFFFFFFF
+
+    def next(self) -> int:
+        self.s = (self.s + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        z = self.s
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+        return z ^ (z >> 31)
+
+    def below(self, m: int, words: int) -> int:
+        x = 0
+        for i in range(words):
+            x |= self.next() << (64 * i)
+        return x % m
+
+    def fr(self) -> int:
+        return self.below(R, 5)
+
+    def fq(self) -> int:
+        return self.below(Q, 7)
