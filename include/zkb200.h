@@ -1,0 +1,143 @@
+/* zkb200 — C ABI of the B200-native Groth16 prover hot path (libzkb200.so).
+ *
+ * Drop-in boundary for the path LayerXcom/zero-chain reaches through
+ *     bellman::groth16::create_random_proof(circuit, &Parameters<Bls12>, rng)
+ * (call sites core/proofs/src/confidential.rs:149, core/proofs/src/anonymous.rs:165; the CRS is
+ * read at core/proofs/src/confidential.rs:95-103 by Parameters::read(buf, checked = true)).
+ * bellman 0.1.0 itself is an un-vendored dependency (Cargo.lock:210-212), so each entry point
+ * cites the upstream function it replaces and the reference call site that reaches it.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the caller owns every input/output buffer for the duration
+ *     of the call; handles (zk_ctx, zk_bases, zk_params) are owned by the library.
+ *   - Fr scalars cross the ABI as canonical FrRepr: 4 little-endian u64 limbs, value < r
+ *     (= Fr::into_repr(), core/pairing/src/bls12_381/fr.rs:290-303).  Montgomery form is internal.
+ *   - the CRS crosses once as the exact Parameters::write byte stream (zface/params/conf_pk.dat);
+ *     proofs come back as the exact Proof::write bytes (core/bellman-verifier/src/lib.rs:55-65).
+ *   - "limb form" points (kernel-level entry points only): affine x|y in Montgomery limbs,
+ *     96 B (G1: x[6] y[6] u64) or 192 B (G2: x.c0 x.c1 y.c0 y.c1), infinity = all zero.
+ *   - every function returns ZK_OK (0) or a negative error; zk_last_error() gives the text.
+ *     Error codes mirror bellman's SynthesisError / io::Error as seen at the call sites
+ *     (zface/src/error.rs:17,45-48).
+ *   - thread safety: a zk_ctx is single-threaded (one CUDA stream); zk_params / zk_bases are
+ *     read-only after creation and may be shared by several contexts on the same device.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     ZK_ERR_CUDA.
+ */
+#ifndef ZKB200_H
+#define ZKB200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZK_OK 0
+#define ZK_ERR_CUDA (-1)                 /* no device / CUDA runtime failure */
+#define ZK_ERR_INVALID (-2)              /* bad argument */
+#define ZK_ERR_ASSIGNMENT_MISSING (-3)   /* SynthesisError::AssignmentMissing: vector sizes do not match the CRS */
+#define ZK_ERR_POLY_DEGREE_TOO_LARGE (-4)/* SynthesisError::PolynomialDegreeTooLarge */
+#define ZK_ERR_UNEXPECTED_IDENTITY (-5)  /* SynthesisError::UnexpectedIdentity (base or delta at infinity) */
+#define ZK_ERR_IO (-6)                   /* SynthesisError::IoError: truncated / malformed Parameters stream */
+#define ZK_ERR_DECODE (-7)               /* GroupDecodingError (not on curve, not in subgroup, bad flags, x >= q) */
+#define ZK_ERR_NOT_CANONICAL (-8)        /* a scalar >= r (PrimeFieldDecodingError::NotInField) */
+
+const char *zk_last_error(void);
+int zk_device_count(void);
+const char *zk_version(void);
+
+/* ---- execution context: one per (device, stream) ------------------------------------------- */
+typedef struct zk_ctx zk_ctx;
+/* stream: a cudaStream_t to run on (e.g. the caller's current stream) or NULL to create one. */
+int zk_ctx_create(int device, void *stream, zk_ctx **out);
+void zk_ctx_destroy(zk_ctx *ctx);
+int zk_ctx_sync(zk_ctx *ctx);
+void *zk_ctx_stream(zk_ctx *ctx);
+
+/* ---- multi-scalar multiplication (replaces bellman::multiexp::multiexp) ----- */
+typedef struct zk_bases zk_bases;
+/* Upload n affine bases (limb form, HOST memory) and, if precompute != 0, build the window tables
+ * 2^(c*w) * P_i on the device (the CRS is fixed, so this is done once, like Parameters::read).
+ * window_bits = 0 picks c from n.  group = 1 (G1) or 2 (G2).  Infinity bases are rejected
+ * (bellman: SynthesisError::UnexpectedIdentity). */
+int zk_bases_upload(zk_ctx *ctx, int group, const uint64_t *bases_limbs, size_t n, int window_bits, int precompute,
+                    zk_bases **out);
+void zk_bases_free(zk_bases *b);
+size_t zk_bases_len(const zk_bases *b);
+int zk_bases_window_bits(const zk_bases *b);
+/* sum_i scalars[i] * P_i over the first n bases.  scalars: canonical FrRepr in HOST memory
+ * (host -> device copy is part of the call); out: uncompressed encoding (96 B for G1, 192 B for G2;
+ * G1Uncompressed / G2Uncompressed::from_affine, core/pairing/src/bls12_381/ec.rs:686-752, 1343-1425). */
+int zk_msm(zk_ctx *ctx, const zk_bases *b, const uint64_t *scalars, size_t n, uint8_t *out);
+/* same with scalars already resident in DEVICE memory (kernel-only timing; prover-internal use) */
+int zk_msm_device(zk_ctx *ctx, const zk_bases *b, const void *d_scalars, size_t n, uint8_t *out);
+/* batch of `batch` independent scalar vectors (each n long, contiguous) against the same bases;
+ * out: batch encodings.  Used by the batched prover. */
+int zk_msm_batch_device(zk_ctx *ctx, const zk_bases *b, const void *d_scalars, size_t n, size_t batch, uint8_t *out);
+/* multi-GPU helper: the partial result as an XYZZ point in DEVICE memory is all-gathered by the
+ * caller (NCCL, bytes) and folded with zk_points_fold: out = encoding of sum of `count` device
+ * points of zk_partial_size(group) bytes each. */
+size_t zk_partial_size(int group);
+int zk_msm_partial_device(zk_ctx *ctx, const zk_bases *b, const void *d_scalars, size_t n, void *d_partial_out);
+int zk_points_fold(zk_ctx *ctx, int group, const void *d_partials, size_t count, uint8_t *out);
+
+/* ---- Fr radix-2 NTT (replaces bellman::domain::EvaluationDomain) ----------- */
+#define ZK_NTT_FFT 0         /* EvaluationDomain::fft        */
+#define ZK_NTT_IFFT 1        /* EvaluationDomain::ifft       (includes the m^-1 scaling) */
+#define ZK_NTT_COSET_FFT 2   /* EvaluationDomain::coset_fft  (distribute_powers(7) then fft) */
+#define ZK_NTT_ICOSET_FFT 3  /* EvaluationDomain::icoset_fft (ifft then distribute_powers(7^-1)) */
+/* data: 2^log_n Fr elements, MONTGOMERY limbs (the in-memory form of bellman's Scalar<E>), natural
+ * order in and out, transformed in place.  Host-memory and device-memory flavours. */
+int zk_ntt_fr(zk_ctx *ctx, uint64_t *data, unsigned log_n, int mode);
+int zk_ntt_fr_device(zk_ctx *ctx, void *d_data, unsigned log_n, int mode);
+
+/* ---- Groth16 (replaces bellman::groth16::{Parameters::read, create_proof}) ------------------ */
+typedef struct zk_params zk_params;
+/* Parses the exact Parameters::write stream (reference call
+ * core/proofs/src/confidential.rs:99 `Parameters::read(&buf[..], true)`), decodes every point on
+ * the device, with checked != 0 also tests on-curve and r-torsion membership
+ * (core/pairing/src/bls12_381/ec.rs:675-685), rejects infinity in the query vectors, and keeps the
+ * CRS (and its MSM window tables) resident on the context's device. */
+int zk_params_load(zk_ctx *ctx, const uint8_t *pk_bytes, size_t len, int checked, zk_params **out);
+void zk_params_free(zk_params *p);
+/* counts[6] = { ic, h, l, a, b_g1, b_g2 } */
+int zk_params_counts(const zk_params *p, uint64_t counts[6]);
+
+/* create_proof for ONE already-synthesised witness (the Rust shim runs ProvingAssignment::synthesize
+ * and the `input_i * 0 = 0` rows, then calls this).
+ *   a/b/c_evals      n_constraints canonical Fr each (<A_j,z>, <B_j,z>, <C_j,z>)
+ *   input_assignment n_inputs canonical Fr, [0] = ONE;  aux_assignment n_aux canonical Fr
+ *   *_density        one BYTE per variable (0/1): DensityTracker bits of the A-aux, B-input, B-aux queries
+ *   r, s             the two blinding scalars create_random_proof draws (canonical)
+ *   proof_out        192 B = Proof::write (compressed A | B | C) */
+int zk_groth16_prove(zk_ctx *ctx, const zk_params *p,
+                     const uint64_t *a_evals, const uint64_t *b_evals, const uint64_t *c_evals, size_t n_constraints,
+                     const uint64_t *input_assignment, size_t n_inputs,
+                     const uint64_t *aux_assignment, size_t n_aux,
+                     const uint8_t *a_aux_density, const uint8_t *b_input_density, const uint8_t *b_aux_density,
+                     const uint64_t r[4], const uint64_t s[4], uint8_t proof_out[192]);
+/* `batch` witnesses of the same circuit (same sizes and densities), arrays concatenated per proof:
+ * a_evals[batch][n_constraints][4] ... r[batch][4], s[batch][4]; proofs_out[batch][192]. */
+int zk_groth16_prove_batch(zk_ctx *ctx, const zk_params *p, size_t batch,
+                           const uint64_t *a_evals, const uint64_t *b_evals, const uint64_t *c_evals, size_t n_constraints,
+                           const uint64_t *input_assignment, size_t n_inputs,
+                           const uint64_t *aux_assignment, size_t n_aux,
+                           const uint8_t *a_aux_density, const uint8_t *b_input_density, const uint8_t *b_aux_density,
+                           const uint64_t *r, const uint64_t *s, uint8_t *proofs_out);
+
+/* ---- utilities / diagnostics ------------------------------------------------------------------ */
+/* out[i] = scalars[i] * base (limb form in, limb form out); group 1 or 2.  Used to build synthetic
+ * CRS / test vectors on the device (fixed-base scalar multiplication). */
+int zk_scalar_mul_many(zk_ctx *ctx, int group, const uint64_t *base_limbs, const uint64_t *scalars, size_t n,
+                       uint64_t *out_limbs);
+/* element-wise field ops on host arrays (parity tests of the device arithmetic):
+ * field 0 = Fq (6 limbs), 1 = Fr (4 limbs); op 0 mul, 1 add, 2 sub, 3 sqr, 4 inverse, 5 from_repr, 6 into_repr */
+int zk_field_op(zk_ctx *ctx, int field, int op, const uint64_t *a, const uint64_t *b, size_t n, uint64_t *out);
+/* calibrates the modmul roofline: runs `iters` dependent-chain-free Montgomery products per thread
+ * over blocks x threads threads, returns products per second (field 0 Fq, 1 Fr). */
+int zk_bench_modmul(zk_ctx *ctx, int field, int blocks, int threads, int iters, double *modmul_per_s, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKB200_H */

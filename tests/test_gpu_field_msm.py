@@ -1,0 +1,145 @@
+"""GPU parity tests (run on the B200 box): device field arithmetic, group law and the Pippenger MSM
+against the oracle, through the C ABI (include/zkb200.h via zero_chain_b200.groth16)."""
+import numpy as np
+import pytest
+
+from oracle import coracle as co
+from oracle import pyref as pr
+from zero_chain_b200 import groth16 as zk
+from zero_chain_b200 import synthetic as sy
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = zk.Context(0)
+    yield c
+    c.close()
+
+
+def _rand_field(mod, nl, n, seed):
+    rng = pr.SplitMix64(seed)
+    edge = [0, 1, 2, mod - 1, mod - 2, (1 << (64 * nl)) % mod, mod >> 1]
+    vals = edge + [rng.below(mod, nl + 1) for _ in range(n - len(edge))]
+    return vals, co.ints_to_limbs(vals, nl)
+
+
+@pytest.mark.parametrize("field,mod,nl", [(zk.FIELD_FQ, pr.Q, 6), (zk.FIELD_FR, pr.R, 4)])
+def test_field_ops_bit_exact(ctx, field, mod, nl):
+    n = 20000
+    va, a = _rand_field(mod, nl, n, 1)
+    vb, b = _rand_field(mod, nl, n, 2)
+    b = np.roll(b, 3, axis=0); vb = vb[-3:] + vb[:-3]
+    bits = 64 * nl
+    rinv = pow(1 << bits, -1, mod)
+    mul = co.limbs_to_ints(zk.field_op(ctx, field, zk.OP_MUL, a, b))
+    add = co.limbs_to_ints(zk.field_op(ctx, field, zk.OP_ADD, a, b))
+    sub = co.limbs_to_ints(zk.field_op(ctx, field, zk.OP_SUB, a, b))
+    sqr = co.limbs_to_ints(zk.field_op(ctx, field, zk.OP_SQR, a))
+    frm = co.limbs_to_ints(zk.field_op(ctx, field, zk.OP_FROM_REPR, a))
+    into = co.limbs_to_ints(zk.field_op(ctx, field, zk.OP_INTO_REPR, a))
+    for i in range(n):
+        x, y = va[i], vb[i]
+        assert mul[i] == x * y * rinv % mod
+        assert add[i] == (x + y) % mod and sub[i] == (x - y) % mod
+        assert sqr[i] == x * x * rinv % mod
+        assert frm[i] == (x << bits) % mod and into[i] == x * rinv % mod
+    inv = co.limbs_to_ints(zk.field_op(ctx, field, zk.OP_INV, a[:64]))
+    for i in range(64):
+        assert inv[i] == (pow(va[i] * rinv, -1, mod) * (1 << bits) % mod if va[i] else 0)
+    # the reference's literal mul KAT through the real PTX path (fq.rs:2564-2588 / fr.rs:1241-1259)
+    import json, os
+    K = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kats.json")))
+    f = "fq" if field == 0 else "fr"
+    g = [sum(int(v, 16) << (64 * i) for i, v in enumerate(x)) for x in K["tests"]["%s.rs::test_%s_mul_assign" % (f, f)]["groups"]]
+    got = co.limbs_to_ints(zk.field_op(ctx, field, zk.OP_MUL, co.ints_to_limbs([g[0]], nl), co.ints_to_limbs([g[1]], nl)))[0]
+    assert got == g[2]
+
+
+@pytest.mark.parametrize("group", [1, 2])
+def test_scalar_mul_many_vs_oracle(ctx, group):
+    rng = pr.SplitMix64(7)
+    ks = [0, 1, 2, pr.R - 1, 0xFFFFFFFF, 1 << 200] + [rng.fr() for _ in range(58)]
+    gen = zk.G1_GENERATOR if group == 1 else zk.G2_GENERATOR
+    assert np.array_equal(gen, co.g1_generator() if group == 1 else co.g2_generator())
+    got = zk.scalar_mul_many(ctx, group, gen, co.ints_to_limbs(ks, 4))
+    want = (co.g1_fixed_base if group == 1 else co.g2_fixed_base)(co.ints_to_limbs(ks, 4))
+    assert np.array_equal(got, want)
+
+
+def _enc(group, p):
+    return (co.g1_encode if group == 1 else co.g2_encode)(p, False)
+
+
+@pytest.mark.parametrize("n,c,tables", [(1, 5, True), (33, 5, True), (1000, 8, True), (1000, 8, False), (4096, 0, True),
+                                        (5000, 13, False), (20000, 16, True), (20000, 0, True)])
+def test_msm_g1_vs_oracle(ctx, n, c, tables):
+    rng = pr.SplitMix64(n * 31 + c)
+    bases = co.g1_fixed_base(sy.random_fr_limbs(n, n))             # random subgroup points
+    scal = sy.random_fr_limbs(n, n + 1)
+    edge = [0, 1, pr.R - 1, 2, (1 << 255) % pr.R, pr.R - (1 << 128)]
+    scal[: min(n, len(edge))] = co.ints_to_limbs(edge[: min(n, len(edge))], 4)
+    b = zk.Bases(ctx, 1, bases, window_bits=c, precompute=tables)
+    got = zk.multiexp(b, scal)
+    assert got == _enc(1, co.g1_msm(bases, scal))
+    b.free()
+
+
+def test_msm_g1_closed_form_and_skew(ctx):
+    # bases (i+1)*G => result (sum s_i (i+1)) G; witness-like scalars: mostly 0/1 (heavy buckets)
+    n = 30000
+    bases = co.g1_fixed_base(co.ints_to_limbs(list(range(1, n + 1)), 4))
+    rng = pr.SplitMix64(5)
+    scal = [(rng.next() & 1) if rng.next() % 10 else rng.fr() for _ in range(n)]
+    k = sum(s * (i + 1) for i, s in enumerate(scal)) % pr.R
+    want = pr.g1_uncompressed(pr.ec_mul(pr.FQ, pr.G1_GEN, k))
+    for c, tables in ((12, True), (10, False)):
+        b = zk.Bases(ctx, 1, bases, window_bits=c, precompute=tables)
+        assert zk.multiexp(b, co.ints_to_limbs(scal, 4)) == want
+        b.free()
+    # repeated bases / cancellation (exceptional cases of the mixed addition)
+    same = np.repeat(bases[:1], 64, axis=0)
+    b = zk.Bases(ctx, 1, same, window_bits=5, precompute=True)
+    assert zk.multiexp(b, co.ints_to_limbs([3] * 64, 4)) == pr.g1_uncompressed(pr.ec_mul(pr.FQ, pr.G1_GEN, 192))
+    assert zk.multiexp(b, co.ints_to_limbs([3, pr.R - 3] * 32, 4)) == pr.g1_uncompressed(pr.INF)
+    b.free()
+
+
+@pytest.mark.parametrize("n,c,tables", [(500, 6, True), (3000, 10, False), (12402, 0, True)])
+def test_msm_g2_vs_oracle(ctx, n, c, tables):
+    bases = co.g2_fixed_base(sy.random_fr_limbs(n, 77 + n))
+    scal = sy.random_fr_limbs(n, 78 + n)
+    scal[:3] = co.ints_to_limbs([0, 1, pr.R - 1], 4)
+    b = zk.Bases(ctx, 2, bases, window_bits=c, precompute=tables)
+    assert zk.multiexp(b, scal) == _enc(2, co.g2_msm(bases, scal))
+    b.free()
+
+
+def test_msm_error_paths(ctx):
+    bases = co.g1_fixed_base(co.ints_to_limbs([1, 2, 3, 4], 4))
+    b = zk.Bases(ctx, 1, bases, window_bits=4)
+    with pytest.raises(zk.ZkError) as e:
+        zk.multiexp(b, co.ints_to_limbs([1, 2, 3, pr.R], 4))          # non-canonical scalar
+    assert e.value.code == -8
+    with pytest.raises(zk.SynthesisError):
+        zk.multiexp(b, co.ints_to_limbs([1, 2, 3], 4))                # size mismatch -> AssignmentMissing
+    bad = bases.copy(); bad[2] = 0
+    with pytest.raises(zk.SynthesisError) as e:
+        zk.Bases(ctx, 1, bad, window_bits=4)                          # infinity base -> UnexpectedIdentity
+    assert e.value.code == -5
+    b.free()
+
+
+def test_msm_batch_matches_single(ctx):
+    import torch
+    n, batch = 3000, 5
+    bases = co.g1_fixed_base(sy.random_fr_limbs(n, 9))
+    b = zk.Bases(ctx, 1, bases, window_bits=9)
+    scal = sy.random_fr_limbs(n * batch, 10).reshape(batch, n, 4)
+    d = torch.from_numpy(scal.view(np.int64)).cuda()
+    torch.cuda.synchronize()
+    got = zk.multiexp_device(b, d.data_ptr(), n, batch)
+    for k in range(batch):
+        assert got[96 * k:96 * k + 96] == _enc(1, co.g1_msm(bases, scal[k]))
+    b.free()

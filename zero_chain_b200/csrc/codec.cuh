@@ -1,0 +1,125 @@
+// Point encodings on the device.  Byte-for-byte the reference's formats:
+//   G1Uncompressed / G1Compressed   core/pairing/src/bls12_381/ec.rs:686-752, 796-867
+//   G2Uncompressed / G2Compressed   core/pairing/src/bls12_381/ec.rs:1343-1425, 1469-1549
+//   PrimeFieldRepr::write_be / read_be   core/pairing/src/lib.rs:408-431
+//   flag bits of byte 0: bit7 compressed, bit6 infinity, bit5 y lexicographically largest
+//   Fq ordering: canonical integers (fq.rs:708-713); Fq2 ordering: c1 first, then c0 (fq2.rs:21-30)
+//   Fq2 wire order: c1 || c0
+#pragma once
+#include "curve.cuh"
+
+namespace zkcodec {
+
+enum { DEC_OK = 0, DEC_COMPRESSION_MODE = 1, DEC_UNEXPECTED_INFO = 2, DEC_COORD = 3, DEC_NOT_ON_CURVE = 4, DEC_NOT_IN_SUBGROUP = 5, DEC_INFINITY = 6 };
+
+ZK_DEV void fq_store_be(uint8_t *out, const Fq &mont) {
+    Fq c = mont.to_canonical();
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        uint32_t w = c.l[11 - i];
+        out[4 * i] = (uint8_t)(w >> 24); out[4 * i + 1] = (uint8_t)(w >> 16); out[4 * i + 2] = (uint8_t)(w >> 8); out[4 * i + 3] = (uint8_t)w;
+    }
+}
+ZK_DEV bool fq_load_be(Fq &out, const uint8_t *in, uint8_t mask0) {
+    Fq c;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        uint32_t b0 = in[4 * i];
+        if (i == 0) b0 &= mask0;
+        c.l[11 - i] = (b0 << 24) | ((uint32_t)in[4 * i + 1] << 16) | ((uint32_t)in[4 * i + 2] << 8) | in[4 * i + 3];
+    }
+    if (!Fq::canonical_lt_mod(c)) return false;
+    out = Fq::from_canonical(c);
+    return true;
+}
+ZK_DEV int canon_cmp(const Fq &a, const Fq &b) {   // compares canonical integers of Montgomery values
+    Fq x = a.to_canonical(), y = b.to_canonical();
+    for (int i = 11; i >= 0; i--) { if (x.l[i] > y.l[i]) return 1; if (x.l[i] < y.l[i]) return -1; }
+    return 0;
+}
+ZK_DEV bool lex_gt_neg(const Fq &y) { return canon_cmp(y, y.neg()) > 0; }
+ZK_DEV bool lex_gt_neg(const Fq2 &y) {
+    Fq2 n = y.neg();
+    int c1 = canon_cmp(y.c1, n.c1);
+    if (c1) return c1 > 0;
+    return canon_cmp(y.c0, n.c0) > 0;
+}
+ZK_DEV void store_coord(uint8_t *out, const Fq &v) { fq_store_be(out, v); }
+ZK_DEV void store_coord(uint8_t *out, const Fq2 &v) { fq_store_be(out, v.c1); fq_store_be(out + 48, v.c0); }
+ZK_DEV bool load_coord(Fq &v, const uint8_t *in, uint8_t mask0) { return fq_load_be(v, in, mask0); }
+ZK_DEV bool load_coord(Fq2 &v, const uint8_t *in, uint8_t mask0) { return fq_load_be(v.c1, in, mask0) && fq_load_be(v.c0, in + 48, 0xff); }
+template <class F> struct CoordBytes;
+template <> struct CoordBytes<Fq> { static constexpr int N = 48; };
+template <> struct CoordBytes<Fq2> { static constexpr int N = 96; };
+
+template <class F>
+ZK_DEV void encode_point(uint8_t *out, const Affine<F> &p, bool compressed) {
+    constexpr int CB = CoordBytes<F>::N;
+    int len = compressed ? CB : 2 * CB;
+    for (int i = 0; i < len; i++) out[i] = 0;
+    if (p.is_inf()) out[0] |= 0x40;
+    else {
+        store_coord(out, p.x);
+        if (!compressed) store_coord(out + CB, p.y);
+        else if (lex_gt_neg(p.y)) out[0] |= 0x20;
+    }
+    if (compressed) out[0] |= 0x80;
+}
+
+ZK_DEV Fq curve_b(const Fq *) { Fq four = Fq::one().dbl().dbl(); return four; }
+ZK_DEV Fq2 curve_b(const Fq2 *) { Fq four = Fq::one().dbl().dbl(); Fq2 r; r.c0 = four; r.c1 = four; return r; }
+template <class F>
+ZK_DEV bool on_curve(const Affine<F> &p) {
+    if (p.is_inf()) return true;
+    return p.y.sqr() == p.x.sqr() * p.x + curve_b((const F *)nullptr);
+}
+template <class F>
+ZK_DEV bool in_subgroup(const Affine<F> &p) {   // r * P == infinity (ec.rs:142-144)
+    uint32_t r[8];
+    for (int i = 0; i < 8; i++) r[i] = FrParams::mod(i);
+    return scalar_mul(XYZZ<F>::from_affine(p), r).is_inf();
+}
+// into_affine / into_affine_unchecked of the Uncompressed encodings
+template <class F>
+ZK_DEV int decode_uncompressed(Affine<F> &p, const uint8_t *in, bool checked) {
+    constexpr int CB = CoordBytes<F>::N;
+    uint8_t b0 = in[0];
+    if (b0 & 0x80) return DEC_COMPRESSION_MODE;
+    if (b0 & 0x40) {
+        if (b0 & 0x3f) return DEC_UNEXPECTED_INFO;
+        for (int i = 1; i < 2 * CB; i++) if (in[i]) return DEC_UNEXPECTED_INFO;
+        p = Affine<F>::inf();
+        return DEC_OK;
+    }
+    if (b0 & 0x20) return DEC_UNEXPECTED_INFO;
+    if (!load_coord(p.x, in, 0x1f) || !load_coord(p.y, in + CB, 0xff)) return DEC_COORD;
+    if (checked) {
+        if (!on_curve(p)) return DEC_NOT_ON_CURVE;
+        if (!in_subgroup(p)) return DEC_NOT_IN_SUBGROUP;
+    }
+    return DEC_OK;
+}
+
+template <class F>
+__global__ void k_encode_xyzz(const XYZZ<F> *__restrict__ in, int n, int compressed, uint8_t *__restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    constexpr int CB = CoordBytes<F>::N;
+    Affine<F> a = in[i].to_affine();
+    encode_point(out + (size_t)i * (compressed ? CB : 2 * CB), a, compressed != 0);
+}
+// decode n uncompressed points; err receives the first non-zero code seen (atomicCAS); reject_inf for query vectors
+template <class F>
+__global__ void __launch_bounds__(128) k_decode_uncompressed(const uint8_t *__restrict__ in, size_t n, int checked, int reject_inf,
+                                                             Affine<F> *__restrict__ out, int *__restrict__ err) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    constexpr int CB = CoordBytes<F>::N;
+    Affine<F> p;
+    int e = decode_uncompressed(p, in + i * 2 * CB, checked != 0);
+    if (!e && reject_inf && p.is_inf()) e = DEC_INFINITY;
+    if (e) { atomicCAS(err, 0, e); return; }
+    out[i] = p;
+}
+
+}  // namespace zkcodec

@@ -62,7 +62,7 @@ struct XYZZ {
     ZK_DEV XYZZ neg() const { XYZZ r = *this; r.y = y.neg(); return r; }
 
     // 2 * (affine p)   (mdbl-2008-s-1)
-    ZK_DEV static XYZZ dbl_affine(const Affine<F> &p) {
+    ZK_PTFN static XYZZ dbl_affine(const Affine<F> &p) {
         if (p.is_inf()) return inf();
         F u = p.y.dbl(), v = u.sqr(), w = u * v, s = p.x * v;
         F xx = p.x.sqr(), m = xx.dbl() + xx;
@@ -73,7 +73,7 @@ struct XYZZ {
         return r;
     }
     // 2 * this   (dbl-2008-s-1)
-    ZK_DEV XYZZ dbl() const {
+    ZK_PTFN XYZZ dbl() const {
         if (is_inf()) return *this;
         F u = y.dbl(), v = u.sqr(), w = u * v, s = x * v;
         F xx = x.sqr(), m = xx.dbl() + xx;
@@ -84,7 +84,7 @@ struct XYZZ {
         return r;
     }
     // this += affine p   (madd-2008-s), p optionally negated by the caller beforehand
-    ZK_DEV void add_mixed(const Affine<F> &p) {
+    ZK_PTFN void add_mixed(const Affine<F> &p) {
         if (p.is_inf()) return;
         if (is_inf()) { x = p.x; y = p.y; zz = F::one(); zzz = F::one(); return; }
         F u2 = p.x * zz, s2 = p.y * zzz;
@@ -100,7 +100,7 @@ struct XYZZ {
         zz = zz * pp; zzz = zzz * ppp;
     }
     // this += o   (add-2008-s)
-    ZK_DEV void add(const XYZZ &o) {
+    ZK_PTFN void add(const XYZZ &o) {
         if (o.is_inf()) return;
         if (is_inf()) { *this = o; return; }
         F u1 = x * o.zz, u2 = o.x * zz, s1 = y * o.zzz, s2 = o.y * zzz;
@@ -116,7 +116,7 @@ struct XYZZ {
         zz = zz * o.zz * pp; zzz = zzz * o.zzz * ppp;
     }
     // canonical affine (one field inversion; into_affine, ec.rs:586-618)
-    ZK_DEV Affine<F> to_affine() const {
+    ZK_PTFN Affine<F> to_affine() const {
         if (is_inf()) return Affine<F>::inf();
         F zi = zzz.inverse();          // 1/ZZZ
         F zi2 = (zi * zz).sqr();       // (ZZ/ZZZ)^2 = 1/ZZ   (ZZ^3 = ZZZ^2)
@@ -126,7 +126,7 @@ struct XYZZ {
 
 // k * P for a canonical 256-bit scalar k (8 LE u32 words), MSB-first double-and-add
 template <class F>
-ZK_DEV XYZZ<F> scalar_mul(const XYZZ<F> &p, const uint32_t *k) {
+ZK_PTFN XYZZ<F> scalar_mul(const XYZZ<F> &p, const uint32_t *k) {
     XYZZ<F> acc = XYZZ<F>::inf();
     bool started = false;
     for (int i = 255; i >= 0; i--) {

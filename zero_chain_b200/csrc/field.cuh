@@ -19,8 +19,22 @@
 #pragma once
 #include <stdint.h>
 
+// Inlining policy.  A Montgomery product is ~770 SASS instructions; inlining it at every call site
+// of the cold paths (G2 arithmetic, scalar multiplication, decoding, reductions) makes ptxas run for
+// tens of minutes.  Translation units that hold the hot kernels define ZK_HOT and get everything
+// inlined; all others call the product and the point operations as real functions.
 #ifdef ZK_HOST_EMUL
 #define ZK_DEV inline
+#define ZK_MULFN inline
+#define ZK_PTFN inline
+#elif defined(ZK_HOT)
+#define ZK_MULFN __device__ __forceinline__
+#define ZK_PTFN __device__ __forceinline__
+#else
+#define ZK_MULFN __device__ __noinline__
+#define ZK_PTFN __device__ __noinline__
+#endif
+#ifdef ZK_HOST_EMUL
 namespace zkprim {
 static thread_local uint32_t cf = 0;
 inline uint32_t add_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b; cf = (uint32_t)(t >> 32); return (uint32_t)t; }
@@ -226,7 +240,7 @@ struct Fp {
         cmad_even(even, [](int j) { return P::modc(j); }, mi);
         odd[N - 1] = addc(odd[N - 1], 0);
     }
-    ZK_DEV friend Fp operator*(const Fp &a, const Fp &b) {
+    ZK_MULFN friend Fp operator*(const Fp &a, const Fp &b) {
         using namespace zkprim;
         uint32_t even[N], odd[N];
         row_first(even, odd, a.l, b.l[0]);
@@ -261,7 +275,7 @@ struct Fp {
         return subc(0, 0) != 0;
     }
     // a^e for a public exponent given as little-endian u32 words (MSB-first square-and-multiply)
-    ZK_DEV Fp pow(const uint32_t *e, int nwords) const {
+    ZK_PTFN Fp pow(const uint32_t *e, int nwords) const {
         Fp acc = one();
         bool started = false;
         for (int i = nwords * 32 - 1; i >= 0; i--) {

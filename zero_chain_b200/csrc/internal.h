@@ -1,0 +1,77 @@
+// Shared host-side declarations of libzkb200 (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "../../include/zkb200.h"
+
+void zk_set_error(const char *fmt, ...);
+#define ZK_CUDA(call)                                                                                  \
+    do {                                                                                               \
+        cudaError_t e__ = (call);                                                                      \
+        if (e__ != cudaSuccess) {                                                                      \
+            zk_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));       \
+            return ZK_ERR_CUDA;                                                                        \
+        }                                                                                              \
+    } while (0)
+#define ZK_TRY(call) do { int r__ = (call); if (r__ != ZK_OK) return r__; } while (0)
+
+// grow-only device buffer
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return ZK_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + (bytes >> 3) + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { zk_set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); return ZK_ERR_CUDA; }
+        cap = want;
+        return ZK_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct zk_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 0;
+    int *d_err = nullptr;          // device error flag (non-canonical scalar etc.)
+    // MSM workspace
+    DevBuf scalars, digits, tile_hist, tile_off, sizes, bucket_off, task_off, scan_scratch, sorted, partials, buckets, red_part, red_x, result, out_bytes;
+    // generic staging
+    DevBuf stage_a, stage_b, stage_c;
+    // NTT workspace
+    DevBuf ntt_tw, ntt_tmp;
+    // groth16 workspace
+    DevBuf g_a, g_b, g_c, g_h, g_scal, g_misc;
+    uint8_t *h_pinned = nullptr;   // small pinned buffer for results
+    size_t h_pinned_cap = 0;
+};
+
+struct zk_bases {
+    int group = 1;       // 1 = G1, 2 = G2
+    int device = 0;
+    size_t n = 0;        // bases (table row stride)
+    int c = 0, W = 0;
+    bool tables = false;
+    void *d_tbl = nullptr;   // [W or 1][n] affine
+};
+
+int zk_use_device(zk_ctx *ctx);
+// internal MSM driver: result XYZZ points (one per batch item) left in ctx->result (device)
+int zk_msm_run(zk_ctx *ctx, const zk_bases *b, const void *d_scalars, size_t n, size_t batch);
+int zk_encode_results(zk_ctx *ctx, int group, size_t count, int compressed, uint8_t *out_host);
+
+// hot-TU launchers (msm_hot.cu)
+void zk_launch_accumulate_g1(const void *bases, const uint32_t *sorted, const uint32_t *bucket_off, const uint32_t *task_off,
+                             uint32_t n_buckets, void *partials, size_t t_max, cudaStream_t st);
+void zk_launch_bench_modmul(int field, int blocks, int threads, int iters, void *sink, cudaStream_t st);
+int zk_bases_from_device(zk_ctx *ctx, int group, const void *d_points, size_t n, int window_bits, int precompute, zk_bases **out);

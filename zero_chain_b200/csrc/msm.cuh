@@ -1,0 +1,306 @@
+// Pippenger multi-scalar multiplication for sm_100a, templated on the base field (Fq -> G1, Fq2 -> G2).
+//
+// Replaces upstream bellman 0.1.0 `multiexp` (call sites in create_proof:
+// H, L, A, B1, B2 — reference call site core/proofs/src/confidential.rs:149).  Same mathematical
+// result (sum s_i * P_i); the schedule is B200-first rather than bellman's per-window CPU tasks:
+//
+//   1. k_msm_digits     scalars (canonical FrRepr) -> signed c-bit digits, layout [window][point]
+//   2. k_tile_hist      per-tile bucket histograms in SHARED MEMORY (2^(c-1) counters, no global atomics)
+//      k_col_scan       per-bucket prefix over tiles;  scan -> bucket offsets
+//      k_scatter        counting-sort scatter with shared-memory cursors -> entries grouped by bucket
+//   3. k_accumulate     one thread per <= TASK_LEN entries of one bucket: gathers affine bases from HBM
+//                       (software-prefetched), mixed additions into an XYZZ accumulator in registers
+//      k_combine        one warp per bucket folds the bucket's task partials
+//   4. k_bit_sums / k_sum_points / k_finish_bits   sum_d d*B[d] as sum_b 2^b (sum of buckets with bit b of d set)
+//
+// "Window sets" (ws) are independent sort/bucket domains: a single MSM over precomputed tables
+// 2^(c*w) * P_i uses ONE ws for all windows (no doubling tail, 2^(c-1) buckets in total); a batch of
+// proofs uses one ws per proof; an ad-hoc MSM without tables uses one ws per window and finishes
+// with a Horner combine.  An entry's payload is always its position inside the ws ([w][i] order),
+// which is also its index into the base table.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "curve.cuh"
+#include "msm_accum.cuh"
+
+namespace zkmsm {
+
+constexpr int TILE = 32768;        // entries per sort tile (u16 tile counters)
+constexpr int SORT_THREADS = 1024;
+constexpr uint32_t DIGIT_ZERO = 0xffffffffu;
+
+// ---- 1. digits ---------------------------------------------------------------------------------
+// scalars: [n_ws][n][8] canonical u32 words (value < r); digits: [n_ws][W][n].
+// Signed digits d_w in (-2^(c-1), 2^(c-1)], sum d_w 2^(c w) = scalar.  Code: (|d|-1) | sign<<31, or DIGIT_ZERO.
+__global__ void k_msm_digits(const uint32_t *__restrict__ scalars, uint32_t n, int c, int W,
+                             uint32_t *__restrict__ digits, int *__restrict__ err) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t ws = blockIdx.y;
+    if (i >= n) return;
+    const uint4 *sp = reinterpret_cast<const uint4 *>(scalars + ((size_t)ws * n + i) * 8);
+    uint4 lo = sp[0], hi = sp[1];
+    uint32_t k[9] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w, 0};
+    {   // canonical check: k < r  (Fr::from_repr rejects otherwise, fr.rs:280-289)
+        Fr t; for (int j = 0; j < 8; j++) t.l[j] = k[j];
+        if (!Fr::canonical_lt_mod(t)) atomicExch(err, 1);
+    }
+    uint32_t carry = 0;
+    const uint32_t half = 1u << (c - 1), full = 1u << c, mask = full - 1;
+    uint32_t *out = digits + (size_t)ws * W * n + i;
+    for (int w = 0; w < W; w++) {
+        int bit = w * c, word = bit >> 5, sh = bit & 31;
+        uint32_t v = 0;
+        if (word < 8) {
+            uint64_t two = (uint64_t)k[word] | ((uint64_t)k[word + 1] << 32);
+            v = (uint32_t)(two >> sh) & mask;
+        }
+        v += carry;
+        uint32_t code;
+        if (v > half) { code = (full - v - 1) | 0x80000000u; carry = 1; }
+        else { code = v ? (v - 1) : DIGIT_ZERO; carry = 0; }
+        out[(size_t)w * n] = code;
+    }
+}
+
+// ---- 2. counting sort --------------------------------------------------------------------------
+__global__ void __launch_bounds__(SORT_THREADS) k_tile_hist(const uint32_t *__restrict__ digits, uint64_t e_ws, int nbins,
+                                                            uint16_t *__restrict__ tile_hist, int tiles_per_ws) {
+    extern __shared__ uint32_t sh[];
+    int tile = blockIdx.x, ws = blockIdx.y;
+    for (int b = threadIdx.x; b < nbins; b += blockDim.x) sh[b] = 0;
+    __syncthreads();
+    uint64_t p0 = (uint64_t)tile * TILE, p1 = p0 + TILE < e_ws ? p0 + TILE : e_ws;
+    const uint32_t *d = digits + (size_t)ws * e_ws;
+    for (uint64_t p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
+        uint32_t code = d[p];
+        if (code != DIGIT_ZERO) atomicAdd(&sh[code & 0x7fffffffu], 1u);
+    }
+    __syncthreads();
+    uint16_t *o = tile_hist + ((size_t)ws * tiles_per_ws + tile) * nbins;
+    for (int b = threadIdx.x; b < nbins; b += blockDim.x) o[b] = (uint16_t)sh[b];
+}
+// thread per (ws, bin): exclusive prefix over tiles -> tile_off, total -> sizes
+__global__ void k_col_scan(const uint16_t *__restrict__ tile_hist, uint32_t *__restrict__ tile_off, uint32_t *__restrict__ sizes,
+                           int nbins, int tiles_per_ws, int n_ws) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nbins * n_ws) return;
+    int ws = g / nbins, b = g - ws * nbins;
+    uint32_t run = 0;
+    for (int t = 0; t < tiles_per_ws; t++) {
+        size_t idx = ((size_t)ws * tiles_per_ws + t) * nbins + b;
+        uint32_t v = tile_hist[idx];
+        tile_off[idx] = run;
+        run += v;
+    }
+    sizes[g] = run;
+}
+__global__ void __launch_bounds__(SORT_THREADS) k_scatter(const uint32_t *__restrict__ digits, uint64_t e_ws, int nbins,
+                                                          const uint32_t *__restrict__ tile_off, const uint32_t *__restrict__ bucket_off,
+                                                          uint32_t *__restrict__ sorted, int tiles_per_ws) {
+    extern __shared__ uint32_t sh[];
+    int tile = blockIdx.x, ws = blockIdx.y;
+    const uint32_t *to = tile_off + ((size_t)ws * tiles_per_ws + tile) * nbins;
+    const uint32_t *bo = bucket_off + (size_t)ws * nbins;
+    for (int b = threadIdx.x; b < nbins; b += blockDim.x) sh[b] = bo[b] + to[b];
+    __syncthreads();
+    uint64_t p0 = (uint64_t)tile * TILE, p1 = p0 + TILE < e_ws ? p0 + TILE : e_ws;
+    const uint32_t *d = digits + (size_t)ws * e_ws;
+    for (uint64_t p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
+        uint32_t code = d[p];
+        if (code != DIGIT_ZERO) {
+            uint32_t pos = atomicAdd(&sh[code & 0x7fffffffu], 1u);
+            sorted[pos] = (uint32_t)p | (code & 0x80000000u);
+        }
+    }
+}
+
+// ---- generic exclusive scan of u32 (three-phase; out[n] = total) -----------------------------------
+constexpr int SCAN_T = 256, SCAN_E = 8, SCAN_B = SCAN_T * SCAN_E;
+template <bool TASKS>
+__device__ __forceinline__ uint32_t scan_load(const uint32_t *in, size_t i) {
+    uint32_t v = in[i];
+    return TASKS ? (v + TASK_LEN - 1) / TASK_LEN : v;
+}
+// TASKS: scan ceil(in/TASK_LEN) instead of in
+template <bool TASKS>
+__global__ void __launch_bounds__(SCAN_T) k_scan_block(const uint32_t *__restrict__ in, uint32_t *__restrict__ out,
+                                                       uint32_t *__restrict__ block_sums, size_t n) {
+    __shared__ uint32_t wsum[SCAN_T / 32];
+    size_t base = (size_t)blockIdx.x * SCAN_B + (size_t)threadIdx.x * SCAN_E;
+    uint32_t v[SCAN_E], s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_E; k++) { v[k] = base + k < n ? scan_load<TASKS>(in, base + k) : 0; s += v[k]; }
+    uint32_t inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if ((threadIdx.x & 31) >= o) inc += t; }
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t w = threadIdx.x < SCAN_T / 32 ? wsum[threadIdx.x] : 0, wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, wi, o); if (threadIdx.x >= o) wi += t; }
+        if (threadIdx.x < SCAN_T / 32) wsum[threadIdx.x] = wi - w;
+        if (threadIdx.x == SCAN_T / 32 - 1 && block_sums) block_sums[blockIdx.x] = wi;
+    }
+    __syncthreads();
+    uint32_t ex = inc - s + wsum[threadIdx.x >> 5];
+#pragma unroll
+    for (int k = 0; k < SCAN_E; k++) { if (base + k < n) out[base + k] = ex; ex += v[k]; }
+}
+__global__ void k_scan_add(uint32_t *__restrict__ out, const uint32_t *__restrict__ block_off, size_t n) {
+    size_t i = (size_t)blockIdx.x * SCAN_B + threadIdx.x;
+    uint32_t o = block_off[blockIdx.x];
+    for (int k = 0; k < SCAN_E; k++, i += SCAN_T) if (i < n) out[i] += o;
+}
+// out[0..n) = exclusive prefix sums of in (or of ceil(in/TASK_LEN) when TASKS), out[n] = total.
+// scratch must hold >= 2 * (n / SCAN_B + 8) words.
+template <bool TASKS>
+inline void exclusive_scan(const uint32_t *in, uint32_t *out, size_t n, uint32_t *scratch, cudaStream_t st) {
+    size_t nb = (n + SCAN_B - 1) / SCAN_B;
+    if (nb == 0) nb = 1;
+    uint32_t *bs = scratch;
+    k_scan_block<TASKS><<<(unsigned)nb, SCAN_T, 0, st>>>(in, out, bs, n);
+    if (nb == 1) {
+        cudaMemcpyAsync(out + n, bs, 4, cudaMemcpyDeviceToDevice, st);
+        return;
+    }
+    uint32_t *bo = scratch + nb + 1;
+    exclusive_scan<false>(bs, bo, nb, bo + nb + 2, st);          // bo[nb] = grand total
+    k_scan_add<<<(unsigned)nb, SCAN_T, 0, st>>>(out, bo, n);
+    cudaMemcpyAsync(out + n, bo + nb, 4, cudaMemcpyDeviceToDevice, st);
+}
+
+// ---- 3. bucket accumulation: k_accumulate lives in msm_accum.cuh (shared with the hot translation unit) ----
+// one warp per bucket: buckets[b] = sum of its task partials
+template <class F>
+__global__ void __launch_bounds__(128) k_combine(const XYZZ<F> *__restrict__ partials, const uint32_t *__restrict__ task_off,
+                                                 uint32_t n_buckets, XYZZ<F> *__restrict__ buckets) {
+    extern __shared__ unsigned char smraw[];
+    XYZZ<F> *sm = reinterpret_cast<XYZZ<F> *>(smraw) + (threadIdx.x >> 5) * 32;
+    uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (b >= n_buckets) return;
+    uint32_t t0 = task_off[b], t1 = task_off[b + 1], nt = t1 - t0;
+    if (nt <= 1) {
+        if (lane == 0) buckets[b] = nt ? partials[t0] : XYZZ<F>::inf();
+        return;
+    }
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t t = t0 + lane; t < t1; t += 32) acc.add(partials[t]);
+    sm[lane] = acc;
+    __syncwarp();
+    for (int o = 16; o > 0; o >>= 1) {
+        if (lane < o) { XYZZ<F> x = sm[lane]; x.add(sm[lane + o]); sm[lane] = x; }
+        __syncwarp();
+    }
+    if (lane == 0) buckets[b] = sm[0];
+}
+
+// ---- 4. bucket reduction: R = sum_{d=1..N} d * B[d-1] ------------------------------------------------
+// Serial point additions are slow on a GPU thread (~10 us each), so the reduction is organised for
+// DEPTH, not work: R = sum_b 2^b X_b with X_b = sum of the buckets whose digit value d has bit b set.
+// The X_b are plain sums (parallel trees, two stages), followed by one short Horner chain per domain.
+//   stage 1: block (slice, bit, dom) -> partial sum of the qualifying buckets of its slice
+//   stage 2: k_sum_points over the slice partials -> X[dom][bit]
+//   stage 3: k_finish_bits: thread per dom, R = X_0 + 2 (X_1 + 2 (X_2 + ...))
+constexpr int RED_T = 128, RED_SLICE = 256;
+template <class F>
+__global__ void __launch_bounds__(RED_T) k_bit_sums(const XYZZ<F> *__restrict__ B, int N, int n_slices, int n_bits,
+                                                    XYZZ<F> *__restrict__ part) {
+    extern __shared__ unsigned char smraw[];
+    XYZZ<F> *sm = reinterpret_cast<XYZZ<F> *>(smraw);
+    int slice = blockIdx.x, bit = blockIdx.y, dom = blockIdx.z;
+    const XYZZ<F> *p = B + (size_t)dom * N;
+    int j0 = slice * RED_SLICE, j1 = j0 + RED_SLICE < N ? j0 + RED_SLICE : N;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (int j = j0 + threadIdx.x; j < j1; j += RED_T)
+        if (((uint32_t)(j + 1) >> bit) & 1u) acc.add(p[j]);
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = RED_T >> 1; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) { XYZZ<F> x = sm[threadIdx.x]; x.add(sm[threadIdx.x + o]); sm[threadIdx.x] = x; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) part[((size_t)dom * n_bits + bit) * n_slices + slice] = sm[0];
+}
+// block per group: out[g] = sum_{j<N} P[g*N + j]
+template <class F>
+__global__ void __launch_bounds__(RED_T) k_sum_points(const XYZZ<F> *__restrict__ P, int N, XYZZ<F> *__restrict__ out) {
+    extern __shared__ unsigned char smraw[];
+    XYZZ<F> *sm = reinterpret_cast<XYZZ<F> *>(smraw);
+    const XYZZ<F> *p = P + (size_t)blockIdx.x * N;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (int j = threadIdx.x; j < N; j += RED_T) acc.add(p[j]);
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = RED_T >> 1; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) { XYZZ<F> x = sm[threadIdx.x]; x.add(sm[threadIdx.x + o]); sm[threadIdx.x] = x; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = sm[0];
+}
+template <class F>
+__global__ void k_finish_bits(const XYZZ<F> *__restrict__ X, int n_bits, int n_dom, XYZZ<F> *__restrict__ R) {
+    int dom = blockIdx.x * blockDim.x + threadIdx.x;
+    if (dom >= n_dom) return;
+    const XYZZ<F> *x = X + (size_t)dom * n_bits;
+    XYZZ<F> r = x[n_bits - 1];
+    for (int b = n_bits - 2; b >= 0; b--) { r = r.dbl(); r.add(x[b]); }
+    R[dom] = r;
+}
+// single thread: out = sum_w 2^(c w) R[w]  (Horner over windows; ad-hoc MSM without tables)
+template <class F>
+__global__ void k_horner_windows(const XYZZ<F> *__restrict__ R, int W, int c, XYZZ<F> *__restrict__ out) {
+    if (threadIdx.x | blockIdx.x) return;
+    XYZZ<F> r = R[W - 1];
+    for (int w = W - 2; w >= 0; w--) {
+        for (int k = 0; k < c; k++) r = r.dbl();
+        r.add(R[w]);
+    }
+    out[0] = r;
+}
+
+// ---- precomputed tables: tbl[w][i] = 2^(c w) P_i (affine), w = 0..W-1 -------------------------------
+// thread handles PRE_K points; per window: c doublings each, then one shared inversion (Montgomery trick).
+constexpr int PRE_K = 4;
+template <class F>
+__global__ void __launch_bounds__(128) k_precompute(Affine<F> *__restrict__ tbl, uint32_t n, int c, int W) {
+    uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * PRE_K;
+    if (i0 >= n) return;
+    int m = n - i0 < PRE_K ? n - i0 : PRE_K;
+    for (int w = 1; w < W; w++) {
+        XYZZ<F> q[PRE_K];
+        F pre[PRE_K];
+        F accz = F::one();
+        for (int k = 0; k < m; k++) {
+            Affine<F> a = tbl[(size_t)(w - 1) * n + i0 + k];
+            XYZZ<F> x = XYZZ<F>::dbl_affine(a);
+            for (int d = 1; d < c; d++) x = x.dbl();
+            q[k] = x;
+            pre[k] = accz;
+            if (!x.is_inf()) accz = accz * x.zzz;
+        }
+        F inv = accz.inverse();
+        for (int k = m - 1; k >= 0; k--) {
+            Affine<F> r;
+            if (q[k].is_inf()) r = Affine<F>::inf();
+            else {
+                F zi = inv * pre[k];           // 1 / ZZZ_k
+                inv = inv * q[k].zzz;
+                F zi2 = (zi * q[k].zz).sqr();  // 1 / ZZ_k
+                r.x = q[k].x * zi2; r.y = q[k].y * zi;
+            }
+            tbl[(size_t)w * n + i0 + k] = r;
+        }
+    }
+}
+
+// ---- output conversion -------------------------------------------------------------------------------
+// thread per point: XYZZ -> canonical affine in Montgomery limb form (all-zero = infinity)
+template <class F>
+__global__ void k_to_affine(const XYZZ<F> *__restrict__ in, Affine<F> *__restrict__ out, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i].to_affine();
+}
+
+}  // namespace zkmsm

@@ -1,0 +1,47 @@
+// Bucket accumulation kernel of the Pippenger MSM (see msm.cuh for the whole schedule).
+// Kept in its own header so the hot translation unit (msm_hot.cu, compiled with ZK_HOT: Montgomery
+// products and the mixed addition fully inlined) and the cold one (G2) share one source.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "curve.cuh"
+
+namespace zkmsm {
+
+constexpr int TASK_LEN = 64;       // max mixed additions per accumulate task
+
+template <class F>
+__device__ __forceinline__ Affine<F> load_affine(const Affine<F> *__restrict__ p) {
+    Affine<F> r;
+    const uint4 *s = reinterpret_cast<const uint4 *>(p);
+    uint4 *d = reinterpret_cast<uint4 *>(&r);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(Affine<F>) / 16); k++) d[k] = __ldg(s + k);
+    return r;
+}
+template <class F>
+__global__ void __launch_bounds__(128) k_accumulate(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ sorted,
+                                                    const uint32_t *__restrict__ bucket_off, const uint32_t *__restrict__ task_off,
+                                                    uint32_t n_buckets, XYZZ<F> *__restrict__ partials) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t n_tasks = task_off[n_buckets];
+    if (t >= n_tasks) return;
+    // bucket of task t: last b with task_off[b] <= t
+    uint32_t lo = 0, hi = n_buckets;
+    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (task_off[mid] <= t) lo = mid; else hi = mid; }
+    uint32_t b = lo, s = t - task_off[b];
+    uint32_t e0 = bucket_off[b] + s * TASK_LEN, e1 = bucket_off[b + 1];
+    if (e1 > e0 + TASK_LEN) e1 = e0 + TASK_LEN;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    uint32_t code = sorted[e0];
+    Affine<F> nxt = load_affine(bases + (code & 0x7fffffffu));
+    for (uint32_t e = e0; e < e1; e++) {
+        Affine<F> p = nxt;
+        bool neg = code >> 31;
+        if (e + 1 < e1) { code = sorted[e + 1]; nxt = load_affine(bases + (code & 0x7fffffffu)); }
+        p.y = p.y.cneg(neg);
+        acc.add_mixed(p);
+    }
+    partials[t] = acc;
+}
+}  // namespace zkmsm
