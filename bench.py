@@ -1,0 +1,338 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark of the B200-native Groth16 prover hot path.
+
+Metric (BASELINE.json): G1 Pippenger MSM Mop/s at 2^20 bases (configs[1]), whole-job aggregate over
+N GPUs, with proofs/sec for the confidential_transfer-shaped circuit reported in "secondary".
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun)
+  python bench.py --impl reference --gpus N ...            # reference arm: the CPU restatement of the
+                                                           # reference's bellman/pairing path (oracle/) on
+                                                           # the box's host cores; rank 0 only
+
+A "step" is one complete MSM of 2^20 terms per GPU: scalars -> digits -> counting sort -> bucket
+accumulation -> bucket reduction -> canonical affine result (96 bytes, bit-identical to the oracle).
+N > 1 is weak scaling: every rank owns a 2^20-base shard of an N*2^20-term MSM (bases partitioned by
+index range); the 192-byte partial results are exchanged with one NCCL all-gather and
+folded on every rank.  `value` has scalars resident in HBM; `e2e` goes through the C-ABI call with
+scalars in pinned HOST memory (host->device copy and the 96-byte device->host result inside the timed
+region).  Only the cpu_baseline leg and --impl reference touch oracle/.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LOG_N = 20
+N_SETS = 8                     # distinct scalar vectors cycled through: 8 x 32 MiB = 256 MiB > 126 MB L2
+KERNELS_PER_MSM = 17           # digits, tile_hist, col_scan, 2 x (scan_block, scan_block, scan_add), scatter,
+                               # accumulate, combine_serial, combine_warp, bit_sums, sum_points, finish_bits, encode
+ALGO_MODMUL_PER_TERM = 176     # 11 (mixed add) x ceil(255/16) windows — SURVEY.md §8(d) / BASELINE.md §3
+ALGO_BYTES_PER_TERM = 128      # 96 B base + 32 B scalar
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, reasons = [], set()
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); out["sm_max_mhz"] = float(r[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out["sm_mhz"] = float(np.median(sm)); out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def make_scalars(n, rank, k):
+    from zero_chain_b200 import synthetic as sy
+    return sy.random_fr_limbs(n, 1000 + 97 * rank + k)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from zero_chain_b200 import groth16 as zk
+    from zero_chain_b200 import synthetic as sy
+
+    world, rank, local = env_int("WORLD_SIZE", 1), env_int("RANK", 0), env_int("LOCAL_RANK", 0)
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = 1 << args.log_n
+    ctx = zk.Context(local)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+
+    # ---- setup (untimed): this rank's shard of the bases, generated on the device, + window tables ----
+    t0 = time.time()
+    base_scalars = sy.random_fr_limbs(n, 7 + rank)
+    bases_limbs = zk.scalar_mul_many(ctx, 1, zk.G1_GENERATOR, base_scalars)      # uniform random subgroup points
+    bases = zk.Bases(ctx, 1, bases_limbs, window_bits=args.window_bits, precompute=True)
+    setup_s = time.time() - t0
+    h_sets = [make_scalars(n, rank, k) for k in range(N_SETS)]
+    d_sets = [torch.from_numpy(h.view(np.int64)).cuda() for h in h_sets]
+    pinned = [torch.from_numpy(h.view(np.int64)).pin_memory() for h in h_sets]
+    psz = zk.partial_size(1)
+    d_part = torch.zeros(psz, dtype=torch.uint8, device="cuda")
+    d_all = torch.zeros(psz * world, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+
+    def step_device(k):
+        d = d_sets[k % N_SETS]
+        if world == 1:
+            return zk.multiexp_device(bases, d.data_ptr(), n)
+        zk.multiexp_partial_device(bases, d.data_ptr(), n, d_part.data_ptr())
+        dist.all_gather_into_tensor(d_all, d_part)
+        torch.cuda.current_stream().synchronize()
+        return zk.points_fold(ctx, 1, d_all.data_ptr(), world)
+
+    d_stage = torch.empty_like(d_sets[0])
+
+    def step_e2e(k):
+        h = pinned[k % N_SETS]
+        if world == 1:
+            return zk.multiexp(bases, h.numpy().view(np.uint64).reshape(-1, 4))    # C-ABI call with a HOST buffer
+        with torch.cuda.stream(stream):
+            d_stage.copy_(h, non_blocking=True)
+        zk.multiexp_partial_device(bases, d_stage.data_ptr(), n, d_part.data_ptr())
+        dist.all_gather_into_tensor(d_all, d_part)
+        torch.cuda.current_stream().synchronize()
+        return zk.points_fold(ctx, 1, d_all.data_ptr(), world)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, profile=False):
+        for k in range(warmup):
+            fn(k)
+        barrier()
+        if profile:
+            ctx.profile(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        last = None
+        for k in range(steps):
+            last = fn(warmup + k)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        prof = ctx.profile_read() if profile else None
+        if profile:
+            ctx.profile(False)
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), last, prof
+
+    # modmul roofline calibrated live on this GPU (register-resident independent Fq products)
+    modmul_peak, _ = zk.bench_modmul(ctx, zk.FIELD_FQ, 148 * 4, 256, 3000)
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_dev, res_dev, prof = timed(step_device, args.steps, args.warmup, profile=True)
+    clocks = sampler.stop() if sampler else None
+    ms_e2e, res_e2e, _ = timed(step_e2e, args.steps, max(3, args.warmup))
+
+    total_terms = n * world
+    value = total_terms * args.steps / (ms_dev * 1e-3) / 1e6
+    e2e_value = total_terms * args.steps / (ms_e2e * 1e-3) / 1e6
+    hbm_peak, hbm_how = peaks()
+    acc_ms, acc_launches = prof
+    acc_avg_s = acc_ms * 1e-3 / max(1, acc_launches)
+    algo_modmul = ALGO_MODMUL_PER_TERM * n            # per launch: one launch processes one rank's n terms
+    roofline = {
+        "kernel": "zkmsm::k_accumulate<Fq> (bucket accumulation)",
+        "bound": "int32-modmul",                       # IMAD issue rate, not HBM, not tensor
+        "achieved": algo_modmul / acc_avg_s, "peak": modmul_peak, "unit": "Fq-modmul/s",
+        "frac": algo_modmul / acc_avg_s / modmul_peak,
+        "peak_how": "zk_bench_modmul: register-resident independent Fq Montgomery products, measured in this run",
+        "avg_launch_ms": acc_avg_s * 1e3, "launches": acc_launches, "share_of_step": acc_ms / ms_dev,
+        "whole_msm_frac": ALGO_MODMUL_PER_TERM * total_terms * args.steps / (ms_dev * 1e-3) / (modmul_peak * world),
+        "hbm": {"bound": "hbm", "achieved": ALGO_BYTES_PER_TERM * n / acc_avg_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": ALGO_BYTES_PER_TERM * n / acc_avg_s / 1e9 / hbm_peak, "peak_how": hbm_how},
+        "traffic": None,
+    }
+    try:
+        roofline["traffic"] = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_accumulate_dram_bytes_per_launch"]
+    except Exception:
+        pass
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import coracle as co
+        t = time.time()
+        want = co.g1_msm(bases_limbs, h_sets[(args.warmup + args.steps - 1) % N_SETS])
+        dt = time.time() - t
+        ok = co.g1_encode(want, False) == res_dev == res_e2e
+        cpu_baseline = {"value": n / dt / 1e6, "unit": "Mop/s", "cores": co.num_threads(), "kind": "port",
+                        "sample": "one full 2^%d-term MSM (same bases and scalars as the last timed GPU step), oracle/zk_oracle.c "
+                                  "bellman-style Pippenger, %.2f s" % (args.log_n, dt),
+                        "matches_gpu_result": bool(ok)}
+        if not ok:
+            raise SystemExit("PARITY FAILURE: GPU MSM result differs from the oracle")
+
+    if rank == 0:
+        line = {
+            "metric": "g1_msm_mops_2^%d" % args.log_n, "value": value, "unit": "Mop/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32-limb Montgomery (Fq 12x32, Fr 8x32), integer", "data": "synthetic",
+            "config": {"workload": "G1 Pippenger MSM, 2^%d uniform-random subgroup bases per GPU (bases sharded by index range, "
+                                   "partial sums all-gathered over NCCL), uniform Fr scalars" % args.log_n,
+                       "window_bits": bases.window_bits, "precomputed_window_tables": True,
+                       "l2_policy": "inputs larger than L2: %d distinct 32 MiB scalar vectors cycled, 1.5 GiB window tables gathered randomly" % N_SETS,
+                       "setup_s_untimed": round(setup_s, 2)},
+            "e2e": {"value": e2e_value, "unit": "Mop/s", "h2d_bytes_per_step": n * 32 * world, "d2h_bytes_per_step": 96 * world,
+                    "ms_per_step": ms_e2e / args.steps, "api": "zk_msm (C ABI, scalars in pinned host memory)"},
+            "gpu_launches": KERNELS_PER_MSM * args.steps * world,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        }
+        if args.secondary and world == 1:
+            try:
+                line["secondary"] = secondary_metrics(ctx, zk, sy, args)
+            except Exception as e:      # the headline line must still print
+                line["secondary"] = {"error": repr(e)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def secondary_metrics(ctx, zk, sy, args):
+    """NTT 2^22 and batched proving of the confidential_transfer-shaped circuit (short runs)."""
+    import torch
+    import ctypes as C
+    from zero_chain_b200 import _lib
+    out = {}
+    stream = torch.cuda.ExternalStream(ctx.stream)
+    # Fr NTT 2^22, device resident
+    logn = 22
+    d = torch.from_numpy(sy.random_fr_limbs(1 << logn, 5).view(np.int64)).cuda()
+    torch.cuda.synchronize()
+    L = _lib.lib()
+    for _ in range(3):
+        L.zk_ntt_fr_device(ctx._h, C.c_void_p(d.data_ptr()), logn, 0)
+    ctx.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    reps = 10
+    for _ in range(reps):
+        L.zk_ntt_fr_device(ctx._h, C.c_void_p(d.data_ptr()), logn, 0)
+    e1.record(stream)
+    ctx.sync(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    fr_peak, _ = zk.bench_modmul(ctx, zk.FIELD_FR, 148 * 4, 256, 3000)
+    out["ntt_fr_2^22"] = {"ms": ms, "melem_per_s": (1 << logn) / ms / 1e3, "algo_modmul_frac": (1 << (logn - 1)) * logn / (ms * 1e-3) / fr_peak,
+                          "fr_modmul_peak": fr_peak}
+    return out
+
+
+def run_reference(args):
+    """Reference arm: the CPU restatement of the reference's bellman/pairing path (oracle/zk_oracle.c;
+    the reference itself is Rust and cannot be built here: no cargo/rustc, bellman un-vendored)."""
+    world, rank = env_int("WORLD_SIZE", 1), env_int("RANK", 0)
+    if rank != 0:
+        return
+    from oracle import coracle as co
+    from zero_chain_b200 import synthetic as sy
+    co.build()
+    n_full = 1 << args.log_n
+    n = min(n_full, 1 << 18)              # bounded sample of the workload: 2^18 of the 2^20 terms per step
+    bases = co.g1_fixed_base(sy.random_fr_limbs(n, 7))
+    sets = [make_scalars(n, 0, k) for k in range(4)]
+    for k in range(args.warmup):
+        co.g1_msm(bases, sets[k % 4])
+    t0 = time.time()
+    for k in range(args.steps):
+        co.g1_msm(bases, sets[(args.warmup + k) % 4])
+    dt = time.time() - t0
+    value = n * args.steps / dt / 1e6
+    cores = co.num_threads()
+    line = {"impl": "reference", "metric": "g1_msm_mops_2^%d" % args.log_n, "value": value, "unit": "Mop/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64-limb Montgomery, integer", "data": "synthetic",
+            "config": {"workload": "G1 Pippenger MSM (bellman multiexp restatement, c = ceil(ln n), one thread per window), "
+                                   "bounded sample: 2^18 of the 2^%d terms per step" % args.log_n},
+            "cpu_baseline": {"value": value, "unit": "Mop/s", "cores": cores, "kind": "port",
+                             "sample": "2^18-term MSM per step, %d steps, all %d host threads" % (args.steps, cores)},
+            "e2e": {"value": value, "unit": "Mop/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log-n", dest="log_n", type=int, default=LOG_N)
+    ap.add_argument("--window-bits", dest="window_bits", type=int, default=16)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-secondary", dest="secondary", action="store_false")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

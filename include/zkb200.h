@@ -137,6 +137,12 @@ int zk_field_op(zk_ctx *ctx, int field, int op, const uint64_t *a, const uint64_
  * over blocks x threads threads, returns products per second (field 0 Fq, 1 Fr). */
 int zk_bench_modmul(zk_ctx *ctx, int field, int blocks, int threads, int iters, double *modmul_per_s, double *ms);
 
+/* Live timing of the dominant kernel (the MSM bucket accumulation) with CUDA events recorded on the
+ * context's stream around each launch: enable, run the workload, read the summed duration and launch
+ * count (bench.py's roofline block).  Disabled by default (no events are created). */
+int zk_ctx_profile(zk_ctx *ctx, int enable);
+int zk_ctx_profile_read(zk_ctx *ctx, double *total_ms, uint64_t *launches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,6 +10,7 @@ void emu_fq_add(const uint32_t *a, const uint32_t *b, uint32_t *o) { Fq x, y; me
 void emu_fq_sub(const uint32_t *a, const uint32_t *b, uint32_t *o) { Fq x, y; memcpy(x.l, a, 48); memcpy(y.l, b, 48); Fq r = x - y; memcpy(o, r.l, 48); }
 void emu_fq_neg(const uint32_t *a, uint32_t *o) { Fq x; memcpy(x.l, a, 48); Fq r = x.neg(); memcpy(o, r.l, 48); }
 void emu_fq_inv(const uint32_t *a, uint32_t *o) { Fq x; memcpy(x.l, a, 48); Fq r = x.inverse(); memcpy(o, r.l, 48); }
+void emu_fq_invf(const uint32_t *a, uint32_t *o) { Fq x; memcpy(x.l, a, 48); Fq r = x.inverse_fermat(); memcpy(o, r.l, 48); }
 void emu_fq_from(const uint32_t *a, uint32_t *o) { Fq x; memcpy(x.l, a, 48); Fq r = Fq::from_canonical(x); memcpy(o, r.l, 48); }
 void emu_fq_to(const uint32_t *a, uint32_t *o) { Fq x; memcpy(x.l, a, 48); Fq r = x.to_canonical(); memcpy(o, r.l, 48); }
 int emu_fq_lt(const uint32_t *a) { Fq x; memcpy(x.l, a, 48); return Fq::canonical_lt_mod(x); }
@@ -18,6 +19,7 @@ void emu_fr_add(const uint32_t *a, const uint32_t *b, uint32_t *o) { Fr x, y; me
 void emu_fr_sub(const uint32_t *a, const uint32_t *b, uint32_t *o) { Fr x, y; memcpy(x.l, a, 32); memcpy(y.l, b, 32); Fr r = x - y; memcpy(o, r.l, 32); }
 void emu_fr_neg(const uint32_t *a, uint32_t *o) { Fr x; memcpy(x.l, a, 32); Fr r = x.neg(); memcpy(o, r.l, 32); }
 void emu_fr_inv(const uint32_t *a, uint32_t *o) { Fr x; memcpy(x.l, a, 32); Fr r = x.inverse(); memcpy(o, r.l, 32); }
+void emu_fr_invf(const uint32_t *a, uint32_t *o) { Fr x; memcpy(x.l, a, 32); Fr r = x.inverse_fermat(); memcpy(o, r.l, 32); }
 void emu_fr_from(const uint32_t *a, uint32_t *o) { Fr x; memcpy(x.l, a, 32); Fr r = Fr::from_canonical(x); memcpy(o, r.l, 32); }
 void emu_fr_to(const uint32_t *a, uint32_t *o) { Fr x; memcpy(x.l, a, 32); Fr r = x.to_canonical(); memcpy(o, r.l, 32); }
 int emu_fr_lt(const uint32_t *a) { Fr x; memcpy(x.l, a, 32); return Fr::canonical_lt_mod(x); }

@@ -45,8 +45,12 @@ def test_field_emulation(emu, f, mod, n, bits):
         assert _call(emu, "emu_%s_neg" % f, n, a) == (-a) % mod
         assert _call(emu, "emu_%s_from" % f, n, a) == (a << bits) % mod
         assert _call(emu, "emu_%s_to" % f, n, a) == a * rinv % mod
-    for a in vals[6:12]:
-        assert _call(emu, "emu_%s_inv" % f, n, a) == pow(a * rinv, -1, mod) * (1 << bits) % mod
+    for a in vals[1:40]:
+        want = pow(a * rinv, -1, mod) * (1 << bits) % mod
+        assert _call(emu, "emu_%s_inv" % f, n, a) == want            # binary extended Euclid (fq.rs:854-907)
+    for a in vals[6:9]:
+        assert _call(emu, "emu_%s_invf" % f, n, a) == pow(a * rinv, -1, mod) * (1 << bits) % mod   # Fermat cross-check
+    assert _call(emu, "emu_%s_inv" % f, n, 0) == 0
     # the reference's own mul KAT (fq.rs:2564-2588 / fr.rs:1241-1259) through the emulated device code
     import json
     K = json.load(open(os.path.join(HERE, "golden", "kats.json")))

@@ -41,6 +41,8 @@ SIGNATURES = {
     "zk_scalar_mul_many": (i32, [vp, i32, vp, vp, sz, vp]),
     "zk_field_op": (i32, [vp, i32, i32, vp, vp, sz, vp]),
     "zk_bench_modmul": (i32, [vp, i32, i32, i32, i32, C.POINTER(dbl), C.POINTER(dbl)]),
+    "zk_ctx_profile": (i32, [vp, i32]),
+    "zk_ctx_profile_read": (i32, [vp, C.POINTER(dbl), C.POINTER(C.c_uint64)]),
 }
 
 _lib = None

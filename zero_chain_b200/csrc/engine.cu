@@ -2,9 +2,7 @@
 // The reference's counterpart is bellman's `multiexp` + `Worker` CPU pool (un-vendored);
 // here the "pool" is one CUDA stream per context and the schedule documented in msm.cuh.
 #include "internal.h"
-#include "msm.cuh"
-#include "codec.cuh"
-#include <type_traits>
+#include "msm_driver.cuh"
 
 using namespace zkmsm;
 
@@ -57,7 +55,7 @@ extern "C" void zk_ctx_destroy(zk_ctx *c) {
 extern "C" int zk_ctx_sync(zk_ctx *c) { ZK_TRY(zk_use_device(c)); ZK_CUDA(cudaStreamSynchronize(c->stream)); return ZK_OK; }
 extern "C" void *zk_ctx_stream(zk_ctx *c) { return (void *)c->stream; }
 
-static int check_err_flag(zk_ctx *ctx) {
+int zk_check_err_flag(zk_ctx *ctx) {
     int e[2] = {0, 0};
     ZK_CUDA(cudaMemcpyAsync(e, ctx->d_err, sizeof(e), cudaMemcpyDeviceToHost, ctx->stream));
     ZK_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -74,7 +72,7 @@ static int check_err_flag(zk_ctx *ctx) {
 static int pick_window(size_t n) {
     int lg = 0;
     while (((size_t)1 << (lg + 1)) <= n) lg++;
-    int c = lg - 2;
+    int c = lg - 1;
     if (c < 5) c = 5;
     if (c > 16) c = 16;
     return c;
@@ -85,13 +83,6 @@ __global__ void k_any_inf(const uint32_t *limbs, size_t n, int words, int *err) 
     uint32_t o = 0;
     for (int k = 0; k < words; k++) o |= limbs[i * words + k];
     if (!o) atomicCAS(err + 1, 0, zkcodec::DEC_INFINITY);
-}
-template <class F>
-static int build_tables(zk_ctx *ctx, zk_bases *b) {
-    unsigned thr = 128, blk = (unsigned)((b->n + thr * PRE_K - 1) / (thr * PRE_K));
-    k_precompute<F><<<blk, thr, 0, ctx->stream>>>((Affine<F> *)b->d_tbl, (uint32_t)b->n, b->c, b->W);
-    ZK_CUDA(cudaGetLastError());
-    return ZK_OK;
 }
 // device-resident variant used by the Groth16 CRS loader: d_points already holds n affine points
 int zk_bases_from_device(zk_ctx *ctx, int group, const void *d_points, size_t n, int window_bits, int precompute, zk_bases **out) {
@@ -110,10 +101,10 @@ int zk_bases_from_device(zk_ctx *ctx, int group, const void *d_points, size_t n,
     if (e != cudaSuccess) { delete b; zk_set_error("cudaMalloc tables (%zu B): %s", rows * n * psz, cudaGetErrorString(e)); return ZK_ERR_CUDA; }
     ZK_CUDA(cudaMemcpyAsync(b->d_tbl, d_points, n * psz, cudaMemcpyDeviceToDevice, ctx->stream));
     k_any_inf<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const uint32_t *)b->d_tbl, n, (int)(psz / 4), ctx->d_err);
-    int r = check_err_flag(ctx);
+    int r = zk_check_err_flag(ctx);
     if (r) { zk_bases_free(b); return r; }
     if (b->tables) {
-        r = group == 1 ? build_tables<Fq>(ctx, b) : build_tables<Fq2>(ctx, b);
+        r = group == 1 ? zk_build_tables_g1(ctx, b) : build_tables_t<Fq2>(ctx, b);
         if (r) { zk_bases_free(b); return r; }
     }
     ZK_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -138,87 +129,7 @@ extern "C" void zk_bases_free(zk_bases *b) {
 extern "C" size_t zk_bases_len(const zk_bases *b) { return b ? b->n : 0; }
 extern "C" int zk_bases_window_bits(const zk_bases *b) { return b ? b->c : 0; }
 
-// ---- MSM driver ------------------------------------------------------------------------------------------
-template <class F>
-static int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t n, size_t batch) {
-    cudaStream_t st = ctx->stream;
-    const int c = b->c, W = b->W, nbins = 1 << (c - 1);
-    // sort domains: with tables one domain per batch item holding all W windows; without tables one per window
-    const bool tables = b->tables;
-    if (!tables && batch != 1) { zk_set_error("batched MSM needs precomputed tables"); return ZK_ERR_INVALID; }
-    const size_t n_dom = tables ? batch : (size_t)W;
-    const uint64_t e_dom = tables ? (uint64_t)n * W : (uint64_t)n;
-    const size_t E = (size_t)n * W * batch;
-    if (E >= ((size_t)1 << 31)) { zk_set_error("MSM too large for 31-bit entry payloads (n*W*batch = %zu)", E); return ZK_ERR_INVALID; }
-    const int tiles = (int)((e_dom + TILE - 1) / TILE);
-    const size_t NB = n_dom * nbins;
-    const size_t t_max = E / TASK_LEN + NB + 1;
-    const size_t pt = sizeof(XYZZ<F>);
-    ZK_TRY(ctx->digits.reserve(E * 4));
-    ZK_TRY(ctx->tile_hist.reserve(n_dom * tiles * (size_t)nbins * 2));
-    ZK_TRY(ctx->tile_off.reserve(n_dom * tiles * (size_t)nbins * 4));
-    ZK_TRY(ctx->sizes.reserve((NB + 1) * 4));
-    ZK_TRY(ctx->bucket_off.reserve((NB + 1) * 4));
-    ZK_TRY(ctx->task_off.reserve((NB + 1) * 4));
-    ZK_TRY(ctx->scan_scratch.reserve((2 * (NB / SCAN_B + 8) + 4096) * 4));
-    ZK_TRY(ctx->sorted.reserve(E * 4));
-    ZK_TRY(ctx->partials.reserve(t_max * pt));
-    ZK_TRY(ctx->buckets.reserve(NB * pt));
-    const int n_bits = c;                      // digit values d in [1, 2^(c-1)] need c bits
-    const int n_slices = (nbins + RED_SLICE - 1) / RED_SLICE;
-    ZK_TRY(ctx->red_part.reserve(n_dom * n_bits * (size_t)n_slices * pt));
-    ZK_TRY(ctx->red_x.reserve(n_dom * n_bits * pt));
-    ZK_TRY(ctx->result.reserve((n_dom + batch + 1) * pt));
-
-    uint32_t *digits = ctx->digits.as<uint32_t>();
-    {   // 1. digits: grid.y = batch item, layout [batch][W][n]
-        dim3 g((unsigned)((n + 255) / 256), (unsigned)batch);
-        k_msm_digits<<<g, 256, 0, st>>>(d_scalars, (uint32_t)n, c, W, digits, ctx->d_err);
-    }
-    // 2. counting sort per domain
-    size_t smem = (size_t)nbins * 4;
-    if (smem > 48 * 1024) {
-        ZK_CUDA(cudaFuncSetAttribute(k_tile_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ZK_CUDA(cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
-    dim3 gs((unsigned)tiles, (unsigned)n_dom);
-    k_tile_hist<<<gs, SORT_THREADS, smem, st>>>(digits, e_dom, nbins, ctx->tile_hist.as<uint16_t>(), tiles);
-    k_col_scan<<<(unsigned)((NB + 255) / 256), 256, 0, st>>>(ctx->tile_hist.as<uint16_t>(), ctx->tile_off.as<uint32_t>(), ctx->sizes.as<uint32_t>(),
-                                                            nbins, tiles, (int)n_dom);
-    exclusive_scan<false>(ctx->sizes.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(), NB, ctx->scan_scratch.as<uint32_t>(), st);
-    exclusive_scan<true>(ctx->sizes.as<uint32_t>(), ctx->task_off.as<uint32_t>(), NB, ctx->scan_scratch.as<uint32_t>(), st);
-    k_scatter<<<gs, SORT_THREADS, smem, st>>>(digits, e_dom, nbins, ctx->tile_off.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(),
-                                              ctx->sorted.as<uint32_t>(), tiles);
-    // 3. accumulate + combine.  The payload of an entry is its position in the domain = [w][i] index;
-    //    with tables that is the table index when n == b->n (checked by the callers).
-    XYZZ<F> *partials = ctx->partials.as<XYZZ<F>>(), *buckets = ctx->buckets.as<XYZZ<F>>();
-    if constexpr (std::is_same<F, Fq>::value)
-        zk_launch_accumulate_g1(b->d_tbl, ctx->sorted.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(), ctx->task_off.as<uint32_t>(), (uint32_t)NB,
-                                partials, t_max, st);
-    else
-        k_accumulate<F><<<(unsigned)((t_max + 127) / 128), 128, 0, st>>>((const Affine<F> *)b->d_tbl, ctx->sorted.as<uint32_t>(),
-                                                                         ctx->bucket_off.as<uint32_t>(), ctx->task_off.as<uint32_t>(), (uint32_t)NB, partials);
-    size_t sm_comb = 4 * 32 * pt;
-    if (sm_comb > 48 * 1024) ZK_CUDA(cudaFuncSetAttribute(k_combine<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_comb));
-    k_combine<F><<<(unsigned)((NB * 32 + 127) / 128), 128, sm_comb, st>>>(partials, ctx->task_off.as<uint32_t>(), (uint32_t)NB, buckets);
-    // 4. bucket reduction per domain
-    size_t sm_red = RED_T * pt;
-    if (sm_red > 48 * 1024) {
-        ZK_CUDA(cudaFuncSetAttribute(k_bit_sums<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_red));
-        ZK_CUDA(cudaFuncSetAttribute(k_sum_points<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_red));
-    }
-    XYZZ<F> *part = ctx->red_part.as<XYZZ<F>>(), *X = ctx->red_x.as<XYZZ<F>>(), *R = ctx->result.as<XYZZ<F>>();
-    k_bit_sums<F><<<dim3((unsigned)n_slices, (unsigned)n_bits, (unsigned)n_dom), RED_T, sm_red, st>>>(buckets, nbins, n_slices, n_bits, part);
-    k_sum_points<F><<<(unsigned)(n_dom * n_bits), RED_T, sm_red, st>>>(part, n_slices, X);
-    if (tables) {
-        k_finish_bits<F><<<(unsigned)((n_dom + 63) / 64), 64, 0, st>>>(X, n_bits, (int)n_dom, R);
-    } else {
-        k_finish_bits<F><<<(unsigned)((n_dom + 63) / 64), 64, 0, st>>>(X, n_bits, (int)n_dom, R + 1);
-        k_horner_windows<F><<<1, 32, 0, st>>>(R + 1, W, c, R);
-    }
-    ZK_CUDA(cudaGetLastError());
-    return ZK_OK;
-}
+// ---- MSM driver: msm_driver.cuh, instantiated for G1 in msm_hot.cu and for G2 here ----
 int zk_msm_run(zk_ctx *ctx, const zk_bases *b, const void *d_scalars, size_t n, size_t batch) {
     if (!ctx || !b || !d_scalars) { zk_set_error("zk_msm: NULL argument"); return ZK_ERR_INVALID; }
     if (b->device != ctx->device) { zk_set_error("bases live on device %d, context on %d", b->device, ctx->device); return ZK_ERR_INVALID; }
@@ -228,18 +139,16 @@ int zk_msm_run(zk_ctx *ctx, const zk_bases *b, const void *d_scalars, size_t n, 
         return ZK_ERR_ASSIGNMENT_MISSING;
     }
     ZK_TRY(zk_use_device(ctx));
-    return b->group == 1 ? msm_run_t<Fq>(ctx, b, (const uint32_t *)d_scalars, n, batch) : msm_run_t<Fq2>(ctx, b, (const uint32_t *)d_scalars, n, batch);
+    return b->group == 1 ? zk_msm_run_g1(ctx, b, (const uint32_t *)d_scalars, n, batch) : msm_run_t<Fq2>(ctx, b, (const uint32_t *)d_scalars, n, batch);
 }
 int zk_encode_results(zk_ctx *ctx, int group, size_t count, int compressed, uint8_t *out_host) {
     size_t per = (group == 1 ? 96 : 192) / (compressed ? 2 : 1);
     ZK_TRY(ctx->out_bytes.reserve(count * per));
     if (count * per > ctx->h_pinned_cap) { zk_set_error("result batch too large"); return ZK_ERR_INVALID; }
-    unsigned blk = (unsigned)((count + 63) / 64);
-    if (group == 1) zkcodec::k_encode_xyzz<Fq><<<blk, 64, 0, ctx->stream>>>(ctx->result.as<G1XYZZ>(), (int)count, compressed, ctx->out_bytes.as<uint8_t>());
-    else zkcodec::k_encode_xyzz<Fq2><<<blk, 64, 0, ctx->stream>>>(ctx->result.as<G2XYZZ>(), (int)count, compressed, ctx->out_bytes.as<uint8_t>());
-    ZK_CUDA(cudaGetLastError());
+    ZK_TRY(group == 1 ? zk_encode_results_g1(ctx, count, compressed, ctx->out_bytes.as<uint8_t>())
+                      : encode_results_t<Fq2>(ctx, count, compressed, ctx->out_bytes.as<uint8_t>()));
     ZK_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->out_bytes.p, count * per, cudaMemcpyDeviceToHost, ctx->stream));
-    ZK_TRY(check_err_flag(ctx));   // synchronises the stream
+    ZK_TRY(zk_check_err_flag(ctx));   // synchronises the stream
     memcpy(out_host, ctx->h_pinned, count * per);
     return ZK_OK;
 }
@@ -263,7 +172,7 @@ extern "C" int zk_msm_partial_device(zk_ctx *ctx, const zk_bases *b, const void 
     if (!d_partial_out) { zk_set_error("zk_msm_partial_device: out is NULL"); return ZK_ERR_INVALID; }
     ZK_TRY(zk_msm_run(ctx, b, d_scalars, n, 1));
     ZK_CUDA(cudaMemcpyAsync(d_partial_out, ctx->result.p, zk_partial_size(b->group), cudaMemcpyDeviceToDevice, ctx->stream));
-    return check_err_flag(ctx);
+    return zk_check_err_flag(ctx);
 }
 template <class F>
 __global__ void k_fold_serial(const XYZZ<F> *in, int n, XYZZ<F> *out) {
@@ -357,5 +266,30 @@ extern "C" int zk_bench_modmul(zk_ctx *ctx, int field, int blocks, int threads, 
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     *per_s = (double)blocks * threads * iters * 4.0 / (ms * 1e-3);
     if (ms_out) *ms_out = ms;
+    return ZK_OK;
+}
+
+// ---- live kernel timing -----------------------------------------------------------------------------------
+extern "C" int zk_ctx_profile(zk_ctx *ctx, int enable) {
+    if (!ctx) { zk_set_error("zk_ctx_profile: NULL ctx"); return ZK_ERR_INVALID; }
+    ZK_TRY(zk_use_device(ctx));
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (cudaEvent_t ev : ctx->prof_events) cudaEventDestroy(ev);
+    ctx->prof_events.clear();
+    ctx->prof_on = enable != 0;
+    return ZK_OK;
+}
+extern "C" int zk_ctx_profile_read(zk_ctx *ctx, double *total_ms, uint64_t *launches) {
+    if (!ctx || !total_ms || !launches) { zk_set_error("zk_ctx_profile_read: NULL argument"); return ZK_ERR_INVALID; }
+    ZK_TRY(zk_use_device(ctx));
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    double tot = 0;
+    for (size_t i = 0; i + 1 < ctx->prof_events.size(); i += 2) {
+        float ms = 0;
+        ZK_CUDA(cudaEventElapsedTime(&ms, ctx->prof_events[i], ctx->prof_events[i + 1]));
+        tot += ms;
+    }
+    *total_ms = tot;
+    *launches = ctx->prof_events.size() / 2;
     return ZK_OK;
 }

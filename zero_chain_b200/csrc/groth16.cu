@@ -1,0 +1,256 @@
+// Groth16 prover orchestration on the device: CRS loading and create_proof below synthesis.
+//
+// Replaces upstream bellman 0.1.0 (un-vendored):
+//   groth16::Parameters::read(reader, checked)   <- core/proofs/src/confidential.rs:95-103
+//   groth16::create_proof(circuit, params, r, s) <- core/proofs/src/confidential.rs:149 (via create_random_proof)
+// and emits Proof::write bytes (core/bellman-verifier/src/lib.rs:55-65).
+//
+// B200-first restructuring of create_proof (same group elements, fewer serial scalar multiplications):
+// the blinding terms are folded into the MSMs by appending vk points to the query vectors at load time,
+//     a'    = a    ++ [alpha_g1, delta_g1]   scalars  inputs ++ aux|A-density ++ [1, r]   -> g_a
+//     b_g1' = b_g1 ++ [beta_g1,  delta_g1]   scalars  inputs|B ++ aux|B       ++ [1, s]   -> g_b1
+//     b_g2' = b_g2 ++ [beta_g2,  delta_g2]   scalars  (same)                              -> g_b
+//     h'    = h    ++ [delta_g1]             scalars  h coefficients ++ [-(r s)]          -> H - rs*delta
+//   g_c = s*g_a + r*g_b1 + (H - rs*delta_g1) + L
+// which equals bellman's  delta*rs + alpha*s + beta*r + A*s + B1*r + H + L.  A whole batch of proofs
+// shares every launch: NTTs are batched (grid.y) and each MSM uses one window set per proof.
+#include "internal.h"
+#include "codec.cuh"
+
+struct zk_params {
+    int device = 0;
+    uint64_t n_ic = 0, n_h = 0, n_l = 0, n_a = 0, n_b1 = 0, n_b2 = 0;
+    zk_bases *h = nullptr, *l = nullptr, *a = nullptr, *b1 = nullptr, *b2 = nullptr;   // extended vectors (see above)
+};
+
+static uint32_t rd_u32be(const uint8_t *p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+
+extern "C" void zk_params_free(zk_params *p) {
+    if (!p) return;
+    zk_bases_free(p->h); zk_bases_free(p->l); zk_bases_free(p->a); zk_bases_free(p->b1); zk_bases_free(p->b2);
+    delete p;
+}
+extern "C" int zk_params_counts(const zk_params *p, uint64_t c[6]) {
+    if (!p || !c) { zk_set_error("zk_params_counts: NULL argument"); return ZK_ERR_INVALID; }
+    c[0] = p->n_ic; c[1] = p->n_h; c[2] = p->n_l; c[3] = p->n_a; c[4] = p->n_b1; c[5] = p->n_b2;
+    return ZK_OK;
+}
+
+extern "C" int zk_params_load(zk_ctx *ctx, const uint8_t *buf, size_t len, int checked, zk_params **out) {
+    if (!ctx || !buf || !out) { zk_set_error("zk_params_load: NULL argument"); return ZK_ERR_INVALID; }
+    ZK_TRY(zk_use_device(ctx));
+    // ---- host: walk the grammar to find the vectors; no arithmetic here ----
+    const size_t VK_FIXED = 96 + 96 + 192 + 192 + 96 + 192;
+    size_t off = VK_FIXED;
+    size_t voff[6], vcnt[6];
+    const size_t vsz[6] = {96, 96, 96, 96, 96, 192};
+    for (int k = 0; k < 6; k++) {
+        if (off + 4 > len) { zk_set_error("Parameters stream truncated (length prefix %d)", k); return ZK_ERR_IO; }
+        vcnt[k] = rd_u32be(buf + off); off += 4;
+        voff[k] = off;
+        if (vcnt[k] > (len - off) / vsz[k]) { zk_set_error("Parameters stream truncated (vector %d: %zu points)", k, vcnt[k]); return ZK_ERR_IO; }
+        off += vcnt[k] * vsz[k];
+    }
+    if (vcnt[1] == 0 || vcnt[2] == 0 || vcnt[3] == 0 || vcnt[4] == 0 || vcnt[5] == 0) { zk_set_error("empty query vector in Parameters"); return ZK_ERR_IO; }
+    // ---- device: decode ----
+    ZK_TRY(ctx->stage_a.reserve(len));
+    ZK_CUDA(cudaMemcpyAsync(ctx->stage_a.p, buf, len, cudaMemcpyHostToDevice, ctx->stream));
+    const uint8_t *d = ctx->stage_a.as<uint8_t>();
+    // extended vectors laid out in stage_b (G1) / stage_c (G2)
+    const size_t n_h = vcnt[1] + 1, n_l = vcnt[2], n_a = vcnt[3] + 2, n_b1 = vcnt[4] + 2, n_b2 = vcnt[5] + 2;
+    ZK_TRY(ctx->stage_b.reserve((n_h + n_l + n_a + n_b1 + vcnt[0] + 8) * sizeof(G1Affine)));
+    ZK_TRY(ctx->stage_c.reserve((n_b2 + 8) * sizeof(G2Affine)));
+    G1Affine *g1 = ctx->stage_b.as<G1Affine>();
+    G1Affine *dh = g1, *dl = dh + n_h, *da = dl + n_l, *db1 = da + n_a, *dic = db1 + n_b1;
+    G2Affine *db2 = ctx->stage_c.as<G2Affine>();
+    int *err = ctx->d_err + 1;
+    auto dec1 = [&](size_t boff, size_t n, G1Affine *dst, int reject_inf) {
+        if (n) zkcodec::k_decode_uncompressed<Fq><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(d + boff, n, checked, reject_inf, dst, err);
+    };
+    auto dec2 = [&](size_t boff, size_t n, G2Affine *dst, int reject_inf) {
+        if (n) zkcodec::k_decode_uncompressed<Fq2><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(d + boff, n, checked, reject_inf, dst, err);
+    };
+    // vk: alpha_g1 @0, beta_g1 @96, beta_g2 @192, gamma_g2 @384, delta_g1 @576, delta_g2 @672
+    dec1(voff[1], vcnt[1], dh, 1);          dec1(576, 1, dh + vcnt[1], 1);                                  // h ++ [delta_g1]
+    dec1(voff[2], vcnt[2], dl, 1);
+    dec1(voff[3], vcnt[3], da, 1);          dec1(0, 1, da + vcnt[3], 1);    dec1(576, 1, da + vcnt[3] + 1, 1);   // a ++ [alpha, delta]
+    dec1(voff[4], vcnt[4], db1, 1);         dec1(96, 1, db1 + vcnt[4], 1);  dec1(576, 1, db1 + vcnt[4] + 1, 1);  // b_g1 ++ [beta_g1, delta]
+    dec2(voff[5], vcnt[5], db2, 1);         dec2(192, 1, db2 + vcnt[5], 1); dec2(672, 1, db2 + vcnt[5] + 1, 1);  // b_g2 ++ [beta_g2, delta_g2]
+    dec1(voff[0], vcnt[0], dic, 0);                                                                       // ic: decoded (validated) only
+    dec2(384, 1, db2 + n_b2, 0);                                                                          // gamma_g2: validated only
+    ZK_CUDA(cudaGetLastError());
+    int r = zk_check_err_flag(ctx);
+    if (r) return r == ZK_ERR_DECODE ? ZK_ERR_DECODE : r;
+    zk_params *p = new zk_params();
+    p->device = ctx->device;
+    p->n_ic = vcnt[0]; p->n_h = vcnt[1]; p->n_l = vcnt[2]; p->n_a = vcnt[3]; p->n_b1 = vcnt[4]; p->n_b2 = vcnt[5];
+    // window tables (built once; the CRS is fixed)
+    if ((r = zk_bases_from_device(ctx, 1, dh, n_h, 0, 1, &p->h)) || (r = zk_bases_from_device(ctx, 1, dl, n_l, 0, 1, &p->l)) ||
+        (r = zk_bases_from_device(ctx, 1, da, n_a, 0, 1, &p->a)) || (r = zk_bases_from_device(ctx, 1, db1, n_b1, 0, 1, &p->b1)) ||
+        (r = zk_bases_from_device(ctx, 2, db2, n_b2, 0, 1, &p->b2))) {
+        zk_params_free(p);
+        return r;
+    }
+    *out = p;
+    return ZK_OK;
+}
+
+// ---- prove -----------------------------------------------------------------------------------------------
+namespace {
+// out[b][k] = src[b][idx[k]]  (32-byte elements)
+__global__ void k_gather32(const uint4 *__restrict__ src, size_t src_stride, const uint32_t *__restrict__ idx, size_t n_idx,
+                           uint4 *__restrict__ dst, size_t dst_stride, size_t dst_off) {
+    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (k >= n_idx) return;
+    const uint4 *s = src + (b * src_stride + idx[k]) * 2;
+    uint4 *d = dst + (b * dst_stride + dst_off + k) * 2;
+    d[0] = s[0]; d[1] = s[1];
+}
+// dst[b][dst_off + j] = terms[b][sel_j]
+__global__ void k_put_terms(const uint4 *__restrict__ terms, int sel0, int sel1, int n_sel, uint4 *__restrict__ dst, size_t dst_stride,
+                            size_t dst_off, size_t batch) {
+    size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    for (int j = 0; j < n_sel; j++) {
+        int sel = j ? sel1 : sel0;
+        const uint4 *s = terms + (b * 4 + sel) * 2;
+        uint4 *d = dst + (b * dst_stride + dst_off + j) * 2;
+        d[0] = s[0]; d[1] = s[1];
+    }
+}
+// thread per (proof, j): T[b][j] = (j == 0 ? s : r) * (j == 0 ? g_a : g_b1)
+__global__ void __launch_bounds__(64) k_scale_points(const G1XYZZ *__restrict__ ga, const G1XYZZ *__restrict__ gb1, const uint32_t *__restrict__ terms,
+                                                     size_t batch, G1XYZZ *__restrict__ T) {
+    size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= 2 * batch) return;
+    size_t b = id >> 1; int j = id & 1;
+    uint32_t k[8];
+    for (int i = 0; i < 8; i++) k[i] = terms[(b * 4 + (j ? 1 : 2)) * 8 + i];     // j=0: s, j=1: r
+    T[id] = scalar_mul(j ? gb1[b] : ga[b], k);
+}
+// thread per proof: g_c = T0 + T1 + H' + L; write Proof (compressed a | b | c)
+__global__ void __launch_bounds__(64) k_finish_proofs(const G1XYZZ *__restrict__ ga, const G2XYZZ *__restrict__ gb, const G1XYZZ *__restrict__ T,
+                                                      const G1XYZZ *__restrict__ H, const G1XYZZ *__restrict__ L, size_t batch, uint8_t *__restrict__ out) {
+    size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    G1XYZZ c = T[2 * b];
+    c.add(T[2 * b + 1]); c.add(H[b]); c.add(L[b]);
+    uint8_t *o = out + b * 192;
+    zkcodec::encode_point(o, ga[b].to_affine(), true);
+    zkcodec::encode_point(o + 48, gb[b].to_affine(), true);
+    zkcodec::encode_point(o + 144, c.to_affine(), true);
+}
+}  // namespace
+
+static int prove_impl(zk_ctx *ctx, const zk_params *p, size_t batch,
+                      const uint64_t *a_ev, const uint64_t *b_ev, const uint64_t *c_ev, size_t n_c,
+                      const uint64_t *inputs, size_t n_in, const uint64_t *aux, size_t n_aux,
+                      const uint8_t *a_aux_d, const uint8_t *b_in_d, const uint8_t *b_aux_d,
+                      const uint64_t *r, const uint64_t *s, uint8_t *proofs_out) {
+    if (!ctx || !p || !a_ev || !b_ev || !c_ev || !inputs || !aux || !a_aux_d || !b_in_d || !b_aux_d || !r || !s || !proofs_out) {
+        zk_set_error("zk_groth16_prove: NULL argument"); return ZK_ERR_INVALID;
+    }
+    if (batch == 0 || batch > 4096 || n_c == 0) { zk_set_error("zk_groth16_prove: bad batch / constraint count"); return ZK_ERR_INVALID; }
+    if (p->device != ctx->device) { zk_set_error("params live on device %d, context on %d", p->device, ctx->device); return ZK_ERR_INVALID; }
+    ZK_TRY(zk_use_device(ctx));
+    cudaStream_t st = ctx->stream;
+    // EvaluationDomain::from_coeffs
+    unsigned log_m = 0; size_t m = 1;
+    while (m < n_c) { m <<= 1; log_m++; if (log_m >= 32) { zk_set_error("PolynomialDegreeTooLarge"); return ZK_ERR_POLY_DEGREE_TOO_LARGE; } }
+    // host-side density bookkeeping (DensityTracker::get_total_density and the query offsets of ParameterSource)
+    std::vector<uint32_t> a_idx, bi_idx, ba_idx;
+    for (size_t i = 0; i < n_aux; i++) { if (a_aux_d[i]) a_idx.push_back((uint32_t)i); if (b_aux_d[i]) ba_idx.push_back((uint32_t)i); }
+    for (size_t i = 0; i < n_in; i++) if (b_in_d[i]) bi_idx.push_back((uint32_t)i);
+    // ParameterSource::get_h / get_l / get_a / get_b_g1 / get_b_g2 size checks
+    if (p->n_h != m - 1 || p->n_l != n_aux || p->n_a != n_in + a_idx.size() || p->n_b1 != bi_idx.size() + ba_idx.size() ||
+        p->n_b2 != p->n_b1 || p->n_ic != n_in) {
+        zk_set_error("witness shape does not match the CRS (h %llu vs %zu, l %llu vs %zu, a %llu vs %zu, b %llu vs %zu, ic %llu vs %zu)",
+                     (unsigned long long)p->n_h, m - 1, (unsigned long long)p->n_l, n_aux, (unsigned long long)p->n_a, n_in + a_idx.size(),
+                     (unsigned long long)p->n_b1, bi_idx.size() + ba_idx.size(), (unsigned long long)p->n_ic, n_in);
+        return ZK_ERR_ASSIGNMENT_MISSING;
+    }
+    const size_t nH = p->n_h + 1, nA = p->n_a + 2, nB = p->n_b1 + 2;
+    // ---- staging ----
+    ZK_TRY(ctx->g_a.reserve(batch * 3 * m * 32));                    // a|b|c domains
+    ZK_TRY(ctx->g_h.reserve(batch * m * 32));                        // quotient
+    ZK_TRY(ctx->g_b.reserve(batch * n_c * 32));                      // raw evals staging
+    ZK_TRY(ctx->g_c.reserve(batch * (n_in + n_aux) * 32 + 64));      // inputs | aux (canonical)
+    size_t max_scal = nH; if (nA > max_scal) max_scal = nA; if (nB > max_scal) max_scal = nB;
+    ZK_TRY(ctx->g_scal.reserve(batch * max_scal * 32));
+    auto rnd = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    size_t misc_bytes = rnd(a_idx.size() * 4 + 4) + rnd(bi_idx.size() * 4 + 4) + rnd(ba_idx.size() * 4 + 4) + 2 * rnd(batch * 32) + rnd(batch * 128) +
+                        4 * rnd(batch * sizeof(G1XYZZ)) + rnd(2 * batch * sizeof(G1XYZZ)) + rnd(batch * sizeof(G2XYZZ)) + rnd(batch * 192);
+    ZK_TRY(ctx->g_misc.reserve(misc_bytes));
+    uint8_t *mp = ctx->g_misc.as<uint8_t>();
+    auto carve = [&](size_t bytes) { uint8_t *q = mp; mp += rnd(bytes); return q; };
+    uint32_t *d_aidx = (uint32_t *)carve(a_idx.size() * 4 + 4), *d_biidx = (uint32_t *)carve(bi_idx.size() * 4 + 4), *d_baidx = (uint32_t *)carve(ba_idx.size() * 4 + 4);
+    uint8_t *d_r = carve(batch * 32), *d_s = carve(batch * 32), *d_terms = carve(batch * 4 * 32);
+    G1XYZZ *d_ga = (G1XYZZ *)carve(batch * sizeof(G1XYZZ)), *d_gb1 = (G1XYZZ *)carve(batch * sizeof(G1XYZZ));
+    G1XYZZ *d_H = (G1XYZZ *)carve(batch * sizeof(G1XYZZ)), *d_L = (G1XYZZ *)carve(batch * sizeof(G1XYZZ)), *d_T = (G1XYZZ *)carve(2 * batch * sizeof(G1XYZZ));
+    G2XYZZ *d_gb = (G2XYZZ *)carve(batch * sizeof(G2XYZZ));
+    uint8_t *d_proofs = carve(batch * 192);
+    if (a_idx.size()) ZK_CUDA(cudaMemcpyAsync(d_aidx, a_idx.data(), a_idx.size() * 4, cudaMemcpyHostToDevice, st));
+    if (bi_idx.size()) ZK_CUDA(cudaMemcpyAsync(d_biidx, bi_idx.data(), bi_idx.size() * 4, cudaMemcpyHostToDevice, st));
+    if (ba_idx.size()) ZK_CUDA(cudaMemcpyAsync(d_baidx, ba_idx.data(), ba_idx.size() * 4, cudaMemcpyHostToDevice, st));
+    ZK_CUDA(cudaMemcpyAsync(d_r, r, batch * 32, cudaMemcpyHostToDevice, st));
+    ZK_CUDA(cudaMemcpyAsync(d_s, s, batch * 32, cudaMemcpyHostToDevice, st));
+    ZK_TRY(zk_fr_blinding_terms(ctx, d_r, d_s, batch, d_terms));
+    // ---- h: 3 x (ifft, coset_fft), quotient, icoset_fft ----
+    const uint64_t *evs[3] = {a_ev, b_ev, c_ev};
+    for (int w = 0; w < 3; w++) {
+        ZK_CUDA(cudaMemcpyAsync(ctx->g_b.p, evs[w], batch * n_c * 32, cudaMemcpyHostToDevice, st));
+        ZK_TRY(zk_fr_load_evals(ctx, ctx->g_b.p, n_c, log_m, w, batch, ctx->g_a.p));
+    }
+    ZK_TRY(zk_ntt_run(ctx, ctx->g_a.p, log_m, ZK_NTT_IFFT, 3 * batch));
+    ZK_TRY(zk_ntt_run(ctx, ctx->g_a.p, log_m, ZK_NTT_COSET_FFT, 3 * batch));
+    ZK_TRY(zk_fr_quotient(ctx, ctx->g_a.p, log_m, batch, ctx->g_h.p));
+    ZK_TRY(zk_ntt_run(ctx, ctx->g_h.p, log_m, ZK_NTT_ICOSET_FFT, batch));
+    // ---- H' = sum h_i * h[i] - rs * delta ----
+    uint4 *scal = ctx->g_scal.as<uint4>();
+    ZK_TRY(zk_fr_into_repr(ctx, ctx->g_h.p, log_m, m - 1, nH, batch, scal));
+    k_put_terms<<<(unsigned)((batch + 63) / 64), 64, 0, st>>>((const uint4 *)d_terms, 3, 3, 1, scal, nH, m - 1, batch);
+    ZK_TRY(zk_msm_run(ctx, p->h, scal, nH, batch));
+    ZK_CUDA(cudaMemcpyAsync(d_H, ctx->result.p, batch * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, st));
+    // ---- assignments ----
+    uint4 *d_in = ctx->g_c.as<uint4>(), *d_aux = d_in + batch * n_in * 2;
+    ZK_CUDA(cudaMemcpyAsync(d_in, inputs, batch * n_in * 32, cudaMemcpyHostToDevice, st));
+    ZK_CUDA(cudaMemcpyAsync(d_aux, aux, batch * n_aux * 32, cudaMemcpyHostToDevice, st));
+    // L
+    ZK_TRY(zk_msm_run(ctx, p->l, d_aux, n_aux, batch));
+    ZK_CUDA(cudaMemcpyAsync(d_L, ctx->result.p, batch * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, st));
+    // g_a: inputs ++ aux|A ++ [1, r]
+    ZK_CUDA(cudaMemcpy2DAsync(scal, nA * 32, d_in, n_in * 32, n_in * 32, batch, cudaMemcpyDeviceToDevice, st));
+    if (a_idx.size()) k_gather32<<<dim3((unsigned)((a_idx.size() + 255) / 256), (unsigned)batch), 256, 0, st>>>(d_aux, n_aux, d_aidx, a_idx.size(), scal, nA, n_in);
+    k_put_terms<<<(unsigned)((batch + 63) / 64), 64, 0, st>>>((const uint4 *)d_terms, 0, 1, 2, scal, nA, nA - 2, batch);
+    ZK_TRY(zk_msm_run(ctx, p->a, scal, nA, batch));
+    ZK_CUDA(cudaMemcpyAsync(d_ga, ctx->result.p, batch * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, st));
+    // g_b1 / g_b: inputs|B ++ aux|B ++ [1, s]
+    if (bi_idx.size()) k_gather32<<<dim3((unsigned)((bi_idx.size() + 255) / 256), (unsigned)batch), 256, 0, st>>>(d_in, n_in, d_biidx, bi_idx.size(), scal, nB, 0);
+    if (ba_idx.size()) k_gather32<<<dim3((unsigned)((ba_idx.size() + 255) / 256), (unsigned)batch), 256, 0, st>>>(d_aux, n_aux, d_baidx, ba_idx.size(), scal, nB, bi_idx.size());
+    k_put_terms<<<(unsigned)((batch + 63) / 64), 64, 0, st>>>((const uint4 *)d_terms, 0, 2, 2, scal, nB, nB - 2, batch);
+    ZK_TRY(zk_msm_run(ctx, p->b1, scal, nB, batch));
+    ZK_CUDA(cudaMemcpyAsync(d_gb1, ctx->result.p, batch * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, st));
+    ZK_TRY(zk_msm_run(ctx, p->b2, scal, nB, batch));
+    ZK_CUDA(cudaMemcpyAsync(d_gb, ctx->result.p, batch * sizeof(G2XYZZ), cudaMemcpyDeviceToDevice, st));
+    // ---- assembly + Proof::write ----
+    k_scale_points<<<(unsigned)((2 * batch + 63) / 64), 64, 0, st>>>(d_ga, d_gb1, (const uint32_t *)d_terms, batch, d_T);
+    k_finish_proofs<<<(unsigned)((batch + 63) / 64), 64, 0, st>>>(d_ga, d_gb, d_T, d_H, d_L, batch, d_proofs);
+    ZK_CUDA(cudaGetLastError());
+    ZK_CUDA(cudaMemcpyAsync(proofs_out, d_proofs, batch * 192, cudaMemcpyDeviceToHost, st));
+    return zk_check_err_flag(ctx);      // synchronises; reports non-canonical scalars
+}
+
+extern "C" int zk_groth16_prove_batch(zk_ctx *ctx, const zk_params *p, size_t batch,
+                                      const uint64_t *a, const uint64_t *b, const uint64_t *c, size_t n_c,
+                                      const uint64_t *inputs, size_t n_in, const uint64_t *aux, size_t n_aux,
+                                      const uint8_t *d1, const uint8_t *d2, const uint8_t *d3,
+                                      const uint64_t *r, const uint64_t *s, uint8_t *out) {
+    return prove_impl(ctx, p, batch, a, b, c, n_c, inputs, n_in, aux, n_aux, d1, d2, d3, r, s, out);
+}
+extern "C" int zk_groth16_prove(zk_ctx *ctx, const zk_params *p,
+                                const uint64_t *a, const uint64_t *b, const uint64_t *c, size_t n_c,
+                                const uint64_t *inputs, size_t n_in, const uint64_t *aux, size_t n_aux,
+                                const uint8_t *d1, const uint8_t *d2, const uint8_t *d3,
+                                const uint64_t r[4], const uint64_t s[4], uint8_t out[192]) {
+    return prove_impl(ctx, p, 1, a, b, c, n_c, inputs, n_in, aux, n_aux, d1, d2, d3, r, s, out);
+}

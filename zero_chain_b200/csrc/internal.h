@@ -52,6 +52,9 @@ struct zk_ctx {
     DevBuf ntt_tw, ntt_tmp;
     // groth16 workspace
     DevBuf g_a, g_b, g_c, g_h, g_scal, g_misc;
+    // live kernel timing (zk_ctx_profile): CUDA events around the dominant kernel on ctx->stream
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_events;   // pairs (start, stop)
     uint8_t *h_pinned = nullptr;   // small pinned buffer for results
     size_t h_pinned_cap = 0;
 };
@@ -70,8 +73,15 @@ int zk_use_device(zk_ctx *ctx);
 int zk_msm_run(zk_ctx *ctx, const zk_bases *b, const void *d_scalars, size_t n, size_t batch);
 int zk_encode_results(zk_ctx *ctx, int group, size_t count, int compressed, uint8_t *out_host);
 
-// hot-TU launchers (msm_hot.cu)
-void zk_launch_accumulate_g1(const void *bases, const uint32_t *sorted, const uint32_t *bucket_off, const uint32_t *task_off,
-                             uint32_t n_buckets, void *partials, size_t t_max, cudaStream_t st);
+// hot-TU entry points (msm_hot.cu)
+int zk_msm_run_g1(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t n, size_t batch);
+int zk_build_tables_g1(zk_ctx *ctx, zk_bases *b);
+int zk_encode_results_g1(zk_ctx *ctx, size_t count, int compressed, uint8_t *d_out);
 void zk_launch_bench_modmul(int field, int blocks, int threads, int iters, void *sink, cudaStream_t st);
 int zk_bases_from_device(zk_ctx *ctx, int group, const void *d_points, size_t n, int window_bits, int precompute, zk_bases **out);
+int zk_ntt_run(zk_ctx *ctx, void *d_data, unsigned log_n, int mode, size_t batch);
+int zk_fr_load_evals(zk_ctx *ctx, const void *d_src, size_t n_c, unsigned log_m, int which, size_t batch, void *d_dst);
+int zk_fr_quotient(zk_ctx *ctx, const void *d_abc, unsigned log_m, size_t batch, void *d_h);
+int zk_fr_into_repr(zk_ctx *ctx, const void *d_h, unsigned log_m, size_t n_out, size_t n_total, size_t batch, void *d_scal);
+int zk_fr_blinding_terms(zk_ctx *ctx, const void *d_r, const void *d_s, size_t batch, void *d_out);
+int zk_check_err_flag(zk_ctx *ctx);

@@ -10,7 +10,7 @@
 //      k_scatter        counting-sort scatter with shared-memory cursors -> entries grouped by bucket
 //   3. k_accumulate     one thread per <= TASK_LEN entries of one bucket: gathers affine bases from HBM
 //                       (software-prefetched), mixed additions into an XYZZ accumulator in registers
-//      k_combine        one warp per bucket folds the bucket's task partials
+//      k_combine_*      fold the bucket's task partials (thread per bucket; warp per heavy bucket)
 //   4. k_bit_sums / k_sum_points / k_finish_bits   sum_d d*B[d] as sum_b 2^b (sum of buckets with bit b of d set)
 //
 // "Window sets" (ws) are independent sort/bucket domains: a single MSM over precomputed tables
@@ -33,7 +33,7 @@ constexpr uint32_t DIGIT_ZERO = 0xffffffffu;
 // ---- 1. digits ---------------------------------------------------------------------------------
 // scalars: [n_ws][n][8] canonical u32 words (value < r); digits: [n_ws][W][n].
 // Signed digits d_w in (-2^(c-1), 2^(c-1)], sum d_w 2^(c w) = scalar.  Code: (|d|-1) | sign<<31, or DIGIT_ZERO.
-__global__ void k_msm_digits(const uint32_t *__restrict__ scalars, uint32_t n, int c, int W,
+static __global__ void k_msm_digits(const uint32_t *__restrict__ scalars, uint32_t n, int c, int W,
                              uint32_t *__restrict__ digits, int *__restrict__ err) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t ws = blockIdx.y;
@@ -64,7 +64,7 @@ __global__ void k_msm_digits(const uint32_t *__restrict__ scalars, uint32_t n, i
 }
 
 // ---- 2. counting sort --------------------------------------------------------------------------
-__global__ void __launch_bounds__(SORT_THREADS) k_tile_hist(const uint32_t *__restrict__ digits, uint64_t e_ws, int nbins,
+static __global__ void __launch_bounds__(SORT_THREADS) k_tile_hist(const uint32_t *__restrict__ digits, uint64_t e_ws, int nbins,
                                                             uint16_t *__restrict__ tile_hist, int tiles_per_ws) {
     extern __shared__ uint32_t sh[];
     int tile = blockIdx.x, ws = blockIdx.y;
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_tile_hist(const uint32_t *__re
     for (int b = threadIdx.x; b < nbins; b += blockDim.x) o[b] = (uint16_t)sh[b];
 }
 // thread per (ws, bin): exclusive prefix over tiles -> tile_off, total -> sizes
-__global__ void k_col_scan(const uint16_t *__restrict__ tile_hist, uint32_t *__restrict__ tile_off, uint32_t *__restrict__ sizes,
+static __global__ void k_col_scan(const uint16_t *__restrict__ tile_hist, uint32_t *__restrict__ tile_off, uint32_t *__restrict__ sizes,
                            int nbins, int tiles_per_ws, int n_ws) {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= nbins * n_ws) return;
@@ -95,7 +95,7 @@ __global__ void k_col_scan(const uint16_t *__restrict__ tile_hist, uint32_t *__r
     }
     sizes[g] = run;
 }
-__global__ void __launch_bounds__(SORT_THREADS) k_scatter(const uint32_t *__restrict__ digits, uint64_t e_ws, int nbins,
+static __global__ void __launch_bounds__(SORT_THREADS) k_scatter(const uint32_t *__restrict__ digits, uint64_t e_ws, int nbins,
                                                           const uint32_t *__restrict__ tile_off, const uint32_t *__restrict__ bucket_off,
                                                           uint32_t *__restrict__ sorted, int tiles_per_ws) {
     extern __shared__ uint32_t sh[];
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_block(const uint32_t *__restric
 #pragma unroll
     for (int k = 0; k < SCAN_E; k++) { if (base + k < n) out[base + k] = ex; ex += v[k]; }
 }
-__global__ void k_scan_add(uint32_t *__restrict__ out, const uint32_t *__restrict__ block_off, size_t n) {
+static __global__ void k_scan_add(uint32_t *__restrict__ out, const uint32_t *__restrict__ block_off, size_t n) {
     size_t i = (size_t)blockIdx.x * SCAN_B + threadIdx.x;
     uint32_t o = block_off[blockIdx.x];
     for (int k = 0; k < SCAN_E; k++, i += SCAN_T) if (i < n) out[i] += o;
@@ -172,19 +172,30 @@ inline void exclusive_scan(const uint32_t *in, uint32_t *out, size_t n, uint32_t
 }
 
 // ---- 3. bucket accumulation: k_accumulate lives in msm_accum.cuh (shared with the hot translation unit) ----
-// one warp per bucket: buckets[b] = sum of its task partials
+// buckets[b] = sum of the bucket's task partials.  Thread per bucket for the common short case (serial
+// adds; a warp with few live lanes wastes its issue slots), one warp per bucket for heavy (skewed) buckets.
+constexpr uint32_t COMB_SERIAL_MAX = 32;
 template <class F>
-__global__ void __launch_bounds__(128) k_combine(const XYZZ<F> *__restrict__ partials, const uint32_t *__restrict__ task_off,
-                                                 uint32_t n_buckets, XYZZ<F> *__restrict__ buckets) {
+__global__ void __launch_bounds__(128) k_combine_serial(const XYZZ<F> *__restrict__ partials, const uint32_t *__restrict__ task_off,
+                                                        uint32_t n_buckets, XYZZ<F> *__restrict__ buckets) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_buckets) return;
+    uint32_t t0 = task_off[b], t1 = task_off[b + 1];
+    if (t1 - t0 > COMB_SERIAL_MAX) return;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    if (t1 > t0) acc = partials[t0];
+    for (uint32_t t = t0 + 1; t < t1; t++) acc.add(partials[t]);
+    buckets[b] = acc;
+}
+template <class F>
+__global__ void __launch_bounds__(128) k_combine_warp(const XYZZ<F> *__restrict__ partials, const uint32_t *__restrict__ task_off,
+                                                      uint32_t n_buckets, XYZZ<F> *__restrict__ buckets) {
     extern __shared__ unsigned char smraw[];
     XYZZ<F> *sm = reinterpret_cast<XYZZ<F> *>(smraw) + (threadIdx.x >> 5) * 32;
     uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (b >= n_buckets) return;
-    uint32_t t0 = task_off[b], t1 = task_off[b + 1], nt = t1 - t0;
-    if (nt <= 1) {
-        if (lane == 0) buckets[b] = nt ? partials[t0] : XYZZ<F>::inf();
-        return;
-    }
+    uint32_t t0 = task_off[b], t1 = task_off[b + 1];
+    if (t1 - t0 <= COMB_SERIAL_MAX) return;
     XYZZ<F> acc = XYZZ<F>::inf();
     for (uint32_t t = t0 + lane; t < t1; t += 32) acc.add(partials[t]);
     sm[lane] = acc;
@@ -203,41 +214,49 @@ __global__ void __launch_bounds__(128) k_combine(const XYZZ<F> *__restrict__ par
 //   stage 1: block (slice, bit, dom) -> partial sum of the qualifying buckets of its slice
 //   stage 2: k_sum_points over the slice partials -> X[dom][bit]
 //   stage 3: k_finish_bits: thread per dom, R = X_0 + 2 (X_1 + 2 (X_2 + ...))
-constexpr int RED_T = 128, RED_SLICE = 256;
+constexpr int RED_T = 128, RED_SLICE = 512;
+// warp-level tree over the 32 lane accumulators of one warp (slot = this warp's 32 shared-memory points)
 template <class F>
-__global__ void __launch_bounds__(RED_T) k_bit_sums(const XYZZ<F> *__restrict__ B, int N, int n_slices, int n_bits,
+__device__ __forceinline__ void warp_tree(XYZZ<F> *slot, XYZZ<F> &acc, uint32_t lane) {
+    slot[lane] = acc;
+    __syncwarp();
+    for (int o = 16; o > 0; o >>= 1) {
+        if (lane < o) { XYZZ<F> x = slot[lane]; x.add(slot[lane + o]); slot[lane] = x; }
+        __syncwarp();
+    }
+    acc = slot[0];
+}
+// one WARP per (slice, bit, dom): lanes stride over the slice's buckets, then a 5-level tree
+template <class F>
+__global__ void __launch_bounds__(RED_T) k_bit_sums(const XYZZ<F> *__restrict__ B, int N, int n_slices, int n_bits, int n_dom,
                                                     XYZZ<F> *__restrict__ part) {
     extern __shared__ unsigned char smraw[];
-    XYZZ<F> *sm = reinterpret_cast<XYZZ<F> *>(smraw);
-    int slice = blockIdx.x, bit = blockIdx.y, dom = blockIdx.z;
+    uint32_t lane = threadIdx.x & 31;
+    XYZZ<F> *slot = reinterpret_cast<XYZZ<F> *>(smraw) + (threadIdx.x >> 5) * 32;
+    size_t gw = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (gw >= (size_t)n_slices * n_bits * n_dom) return;
+    int slice = (int)(gw % n_slices), bit = (int)((gw / n_slices) % n_bits), dom = (int)(gw / ((size_t)n_slices * n_bits));
     const XYZZ<F> *p = B + (size_t)dom * N;
     int j0 = slice * RED_SLICE, j1 = j0 + RED_SLICE < N ? j0 + RED_SLICE : N;
     XYZZ<F> acc = XYZZ<F>::inf();
-    for (int j = j0 + threadIdx.x; j < j1; j += RED_T)
+    for (int j = j0 + (int)lane; j < j1; j += 32)
         if (((uint32_t)(j + 1) >> bit) & 1u) acc.add(p[j]);
-    sm[threadIdx.x] = acc;
-    __syncthreads();
-    for (int o = RED_T >> 1; o > 0; o >>= 1) {
-        if ((int)threadIdx.x < o) { XYZZ<F> x = sm[threadIdx.x]; x.add(sm[threadIdx.x + o]); sm[threadIdx.x] = x; }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) part[((size_t)dom * n_bits + bit) * n_slices + slice] = sm[0];
+    warp_tree(slot, acc, lane);
+    if (lane == 0) part[((size_t)dom * n_bits + bit) * n_slices + slice] = acc;
 }
-// block per group: out[g] = sum_{j<N} P[g*N + j]
+// one WARP per group: out[g] = sum_{j<N} P[g*N + j]
 template <class F>
-__global__ void __launch_bounds__(RED_T) k_sum_points(const XYZZ<F> *__restrict__ P, int N, XYZZ<F> *__restrict__ out) {
+__global__ void __launch_bounds__(RED_T) k_sum_points(const XYZZ<F> *__restrict__ P, int N, int n_groups, XYZZ<F> *__restrict__ out) {
     extern __shared__ unsigned char smraw[];
-    XYZZ<F> *sm = reinterpret_cast<XYZZ<F> *>(smraw);
-    const XYZZ<F> *p = P + (size_t)blockIdx.x * N;
+    uint32_t lane = threadIdx.x & 31;
+    XYZZ<F> *slot = reinterpret_cast<XYZZ<F> *>(smraw) + (threadIdx.x >> 5) * 32;
+    size_t g = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (g >= (size_t)n_groups) return;
+    const XYZZ<F> *p = P + g * N;
     XYZZ<F> acc = XYZZ<F>::inf();
-    for (int j = threadIdx.x; j < N; j += RED_T) acc.add(p[j]);
-    sm[threadIdx.x] = acc;
-    __syncthreads();
-    for (int o = RED_T >> 1; o > 0; o >>= 1) {
-        if ((int)threadIdx.x < o) { XYZZ<F> x = sm[threadIdx.x]; x.add(sm[threadIdx.x + o]); sm[threadIdx.x] = x; }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) out[blockIdx.x] = sm[0];
+    for (int j = lane; j < N; j += 32) acc.add(p[j]);
+    warp_tree(slot, acc, lane);
+    if (lane == 0) out[g] = acc;
 }
 template <class F>
 __global__ void k_finish_bits(const XYZZ<F> *__restrict__ X, int n_bits, int n_dom, XYZZ<F> *__restrict__ R) {

@@ -1,0 +1,107 @@
+// Host-side MSM driver, templated on the base field so that G1 is compiled in the hot translation unit
+// (msm_hot.cu, everything inlined) and G2 in the cold one (engine.cu).  See msm.cuh for the schedule.
+#pragma once
+#include "internal.h"
+#include "msm.cuh"
+#include "codec.cuh"
+
+namespace zkmsm {
+
+template <class F>
+int build_tables_t(zk_ctx *ctx, zk_bases *b) {
+    unsigned thr = 128, blk = (unsigned)((b->n + thr * PRE_K - 1) / (thr * PRE_K));
+    k_precompute<F><<<blk, thr, 0, ctx->stream>>>((Affine<F> *)b->d_tbl, (uint32_t)b->n, b->c, b->W);
+    ZK_CUDA(cudaGetLastError());
+    return ZK_OK;
+}
+
+template <class F>
+int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t n, size_t batch) {
+    cudaStream_t st = ctx->stream;
+    const int c = b->c, W = b->W, nbins = 1 << (c - 1);
+    // sort domains: with tables one domain per batch item holding all W windows; without tables one per window
+    const bool tables = b->tables;
+    if (!tables && batch != 1) { zk_set_error("batched MSM needs precomputed tables"); return ZK_ERR_INVALID; }
+    const size_t n_dom = tables ? batch : (size_t)W;
+    const uint64_t e_dom = tables ? (uint64_t)n * W : (uint64_t)n;
+    const size_t E = (size_t)n * W * batch;
+    if (E >= ((size_t)1 << 31)) { zk_set_error("MSM too large for 31-bit entry payloads (n*W*batch = %zu)", E); return ZK_ERR_INVALID; }
+    const int tiles = (int)((e_dom + TILE - 1) / TILE);
+    const size_t NB = n_dom * nbins;
+    const size_t t_max = E / TASK_LEN + NB + 1;
+    const size_t pt = sizeof(XYZZ<F>);
+    ZK_TRY(ctx->digits.reserve(E * 4));
+    ZK_TRY(ctx->tile_hist.reserve(n_dom * tiles * (size_t)nbins * 2));
+    ZK_TRY(ctx->tile_off.reserve(n_dom * tiles * (size_t)nbins * 4));
+    ZK_TRY(ctx->sizes.reserve((NB + 1) * 4));
+    ZK_TRY(ctx->bucket_off.reserve((NB + 1) * 4));
+    ZK_TRY(ctx->task_off.reserve((NB + 1) * 4));
+    ZK_TRY(ctx->scan_scratch.reserve((2 * (NB / SCAN_B + 8) + 4096) * 4));
+    ZK_TRY(ctx->sorted.reserve(E * 4));
+    ZK_TRY(ctx->partials.reserve(t_max * pt));
+    ZK_TRY(ctx->buckets.reserve(NB * pt));
+    const int n_bits = c;                      // digit values d in [1, 2^(c-1)] need c bits
+    const int n_slices = (nbins + RED_SLICE - 1) / RED_SLICE;
+    ZK_TRY(ctx->red_part.reserve(n_dom * n_bits * (size_t)n_slices * pt));
+    ZK_TRY(ctx->red_x.reserve(n_dom * n_bits * pt));
+    ZK_TRY(ctx->result.reserve((n_dom + batch + 1) * pt));
+
+    uint32_t *digits = ctx->digits.as<uint32_t>();
+    {   // 1. digits: grid.y = batch item, layout [batch][W][n]
+        dim3 g((unsigned)((n + 255) / 256), (unsigned)batch);
+        k_msm_digits<<<g, 256, 0, st>>>(d_scalars, (uint32_t)n, c, W, digits, ctx->d_err);
+    }
+    // 2. counting sort per domain
+    size_t smem = (size_t)nbins * 4;
+    if (smem > 48 * 1024) {
+        ZK_CUDA(cudaFuncSetAttribute(k_tile_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ZK_CUDA(cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    dim3 gs((unsigned)tiles, (unsigned)n_dom);
+    k_tile_hist<<<gs, SORT_THREADS, smem, st>>>(digits, e_dom, nbins, ctx->tile_hist.as<uint16_t>(), tiles);
+    k_col_scan<<<(unsigned)((NB + 255) / 256), 256, 0, st>>>(ctx->tile_hist.as<uint16_t>(), ctx->tile_off.as<uint32_t>(), ctx->sizes.as<uint32_t>(),
+                                                            nbins, tiles, (int)n_dom);
+    exclusive_scan<false>(ctx->sizes.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(), NB, ctx->scan_scratch.as<uint32_t>(), st);
+    exclusive_scan<true>(ctx->sizes.as<uint32_t>(), ctx->task_off.as<uint32_t>(), NB, ctx->scan_scratch.as<uint32_t>(), st);
+    k_scatter<<<gs, SORT_THREADS, smem, st>>>(digits, e_dom, nbins, ctx->tile_off.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(),
+                                              ctx->sorted.as<uint32_t>(), tiles);
+    // 3. accumulate + combine.  The payload of an entry is its position in the domain = [w][i] index;
+    //    with tables that is the table index when n == b->n (checked by the callers).
+    XYZZ<F> *partials = ctx->partials.as<XYZZ<F>>(), *buckets = ctx->buckets.as<XYZZ<F>>();
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (ctx->prof_on) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, st); }
+    k_accumulate<F><<<(unsigned)((t_max + 127) / 128), 128, 0, st>>>((const Affine<F> *)b->d_tbl, ctx->sorted.as<uint32_t>(),
+                                                                     ctx->bucket_off.as<uint32_t>(), ctx->task_off.as<uint32_t>(), (uint32_t)NB, partials);
+    if (ctx->prof_on) { cudaEventRecord(ev1, st); ctx->prof_events.push_back(ev0); ctx->prof_events.push_back(ev1); }
+    const size_t sm_warp = 4 * 32 * pt;      // 4 warps x 32 points
+    if (sm_warp > 48 * 1024) {
+        ZK_CUDA(cudaFuncSetAttribute(k_combine_warp<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_warp));
+        ZK_CUDA(cudaFuncSetAttribute(k_bit_sums<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_warp));
+        ZK_CUDA(cudaFuncSetAttribute(k_sum_points<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_warp));
+    }
+    k_combine_serial<F><<<(unsigned)((NB + 127) / 128), 128, 0, st>>>(partials, ctx->task_off.as<uint32_t>(), (uint32_t)NB, buckets);
+    k_combine_warp<F><<<(unsigned)((NB * 32 + 127) / 128), 128, sm_warp, st>>>(partials, ctx->task_off.as<uint32_t>(), (uint32_t)NB, buckets);
+    // 4. bucket reduction per domain
+    XYZZ<F> *part = ctx->red_part.as<XYZZ<F>>(), *X = ctx->red_x.as<XYZZ<F>>(), *R = ctx->result.as<XYZZ<F>>();
+    size_t n_w = (size_t)n_slices * n_bits * n_dom;
+    k_bit_sums<F><<<(unsigned)((n_w * 32 + RED_T - 1) / RED_T), RED_T, sm_warp, st>>>(buckets, nbins, n_slices, n_bits, (int)n_dom, part);
+    size_t n_g = n_dom * n_bits;
+    k_sum_points<F><<<(unsigned)((n_g * 32 + RED_T - 1) / RED_T), RED_T, sm_warp, st>>>(part, n_slices, (int)n_g, X);
+    if (tables) {
+        k_finish_bits<F><<<(unsigned)((n_dom + 31) / 32), 32, 0, st>>>(X, n_bits, (int)n_dom, R);
+    } else {
+        k_finish_bits<F><<<(unsigned)((n_dom + 31) / 32), 32, 0, st>>>(X, n_bits, (int)n_dom, R + 1);
+        k_horner_windows<F><<<1, 32, 0, st>>>(R + 1, W, c, R);
+    }
+    ZK_CUDA(cudaGetLastError());
+    return ZK_OK;
+}
+
+template <class F>
+int encode_results_t(zk_ctx *ctx, size_t count, int compressed, uint8_t *d_out) {
+    zkcodec::k_encode_xyzz<F><<<(unsigned)((count + 31) / 32), 32, 0, ctx->stream>>>(ctx->result.as<XYZZ<F>>(), (int)count, compressed, d_out);
+    ZK_CUDA(cudaGetLastError());
+    return ZK_OK;
+}
+
+}  // namespace zkmsm

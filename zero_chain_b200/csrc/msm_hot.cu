@@ -1,16 +1,13 @@
-// Hot translation unit: kernels whose Montgomery products / point additions are fully inlined
-// (ZK_HOT).  Everything else in the library calls them as functions (see field.cuh, inlining policy).
+// Hot translation unit: G1 MSM driver + kernels with Montgomery products / point additions fully
+// inlined (ZK_HOT).  Everything else in the library calls them as functions (field.cuh, inlining policy).
 #define ZK_HOT 1
-#include "internal.h"
-#include "msm_accum.cuh"
+#include "msm_driver.cuh"
 
 using namespace zkmsm;
 
-void zk_launch_accumulate_g1(const void *bases, const uint32_t *sorted, const uint32_t *bucket_off, const uint32_t *task_off,
-                             uint32_t n_buckets, void *partials, size_t t_max, cudaStream_t st) {
-    k_accumulate<Fq><<<(unsigned)((t_max + 127) / 128), 128, 0, st>>>((const G1Affine *)bases, sorted, bucket_off, task_off, n_buckets,
-                                                                     (G1XYZZ *)partials);
-}
+int zk_msm_run_g1(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t n, size_t batch) { return msm_run_t<Fq>(ctx, b, d_scalars, n, batch); }
+int zk_build_tables_g1(zk_ctx *ctx, zk_bases *b) { return build_tables_t<Fq>(ctx, b); }
+int zk_encode_results_g1(zk_ctx *ctx, size_t count, int compressed, uint8_t *d_out) { return encode_results_t<Fq>(ctx, count, compressed, d_out); }
 
 // modmul roofline calibration: 4 independent chains per thread, register resident
 template <class T>

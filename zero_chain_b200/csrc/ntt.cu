@@ -1,0 +1,317 @@
+// Radix-2 NTT over the BLS12-381 scalar field Fr for sm_100a.
+//
+// Replaces upstream bellman 0.1.0 `EvaluationDomain::{fft, ifft, coset_fft, icoset_fft}` (SURVEY.md
+// §3.2, §8 a7; reached from create_proof, reference call site core/proofs/src/confidential.rs:149).
+// Same definition — out[k] = sum_j a[j] w^(jk), w = ROOT_OF_UNITY^(2^(32-log_n)) (fr.rs:47-55),
+// coset generator 7 (fr.rs:38-44), ifft scaled by m^-1 — so results are bit-identical; the schedule
+// is B200-first instead of bellman's serial bit-reversal + log n global butterfly rounds:
+//
+//   four-step split N = N1 x N2 (log N1 = floor(k/2)): two kernels, each doing a complete
+//   sub-transform of <= 2048 points in SHARED MEMORY (decimation in frequency, in place),
+//     pass A  columns (stride N2): [x g^i] -> N1-point DFT -> x w^(n2 m1) -> back in place
+//     pass B  rows (contiguous):   N2-point DFT -> [x g^-i m^-1 | x m^-1] -> transposed store
+//   The bit-reversal is never materialised: each pass reads its DIF result out of shared memory in
+//   bit-reversed order, and adjacent columns / rows are grouped per block so global accesses are
+//   COLS*32 B / ROWS*32 B contiguous.  Twiddles come from per-size tables (w^i, g^i, g^-i/m) built
+//   once per context and log_n; the kernel is bound by the Fr Montgomery products
+//   (k/2 + ~1.1 per element), not by HBM (3 x 32 B per element per pass).
+//   A batch of transforms of the same size (the prover's 7 per proof) is one launch (grid.y).
+#define ZK_HOT 1
+#include "internal.h"
+#include "field.cuh"
+
+namespace {
+
+constexpr int NTT_THREADS = 256;
+constexpr int MAX_TILE_LOG = 11;    // 2048 elements * 32 B = 64 KB of shared memory
+
+// Fr constants in Montgomery form (fr.rs:38-55)
+__device__ __forceinline__ Fr fr_generator() {
+    Fr g; const uint32_t v[8] = {0xfffffff1u, 0x0000000eu, 0x00189c0fu, 0x17e363d3u, 0x6f8457b0u, 0xff9c5787u, 0x8fc5a8c4u, 0x35133220u};
+    for (int i = 0; i < 8; i++) g.l[i] = v[i];
+    return g;
+}
+__device__ __forceinline__ Fr fr_root_of_unity() {
+    Fr g; const uint32_t v[8] = {0x5f0e466au, 0xb9b58d8cu, 0x1819d7ecu, 0x5b1b4c80u, 0x52a31e64u, 0x0af53ae3u, 0x19e9b27bu, 0x5bf3addau};
+    for (int i = 0; i < 8; i++) g.l[i] = v[i];
+    return g;
+}
+__device__ __forceinline__ Fr fr_generator_inv() {   // 7^-1
+    Fr g; const uint32_t v[8] = {0xdb6db6dcu, 0xdb6db6dau, 0xdb6cc6dau, 0xe6b5824au, 0x05810db9u, 0xf8b356e0u, 0x60ec4796u, 0x66d0f1e6u};
+    for (int i = 0; i < 8; i++) g.l[i] = v[i];
+    return g;
+}
+__device__ __forceinline__ Fr fr_inv2() {            // 2^-1
+    Fr g; const uint32_t v[8] = {0xffffffffu, 0x00000000u, 0x0001a401u, 0xac425bfdu, 0xf65e27fau, 0xccc627f7u, 0xd66282b7u, 0x0c1258acu};
+    for (int i = 0; i < 8; i++) g.l[i] = v[i];
+    return g;
+}
+__device__ __forceinline__ Fr fr_pow_u64(Fr base, uint64_t e) {
+    Fr acc = Fr::one();
+    while (e) { if (e & 1) acc = acc * base; base = base * base; e >>= 1; }
+    return acc;
+}
+__device__ __forceinline__ Fr load_fr(const Fr *p) {
+    const uint4 *s = reinterpret_cast<const uint4 *>(p);
+    uint4 a = s[0], b = s[1];
+    Fr r; r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w; r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void store_fr(Fr *p, const Fr &v) {
+    uint4 *d = reinterpret_cast<uint4 *>(p);
+    d[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    d[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+
+// tables: W[i] = w^i, G[i] = g^i, GI[i] = g^-i * m^-1, i < N;  consts[0] = m^-1, consts[1] = (g^m - 1)^-1
+__global__ void k_ntt_tables(Fr *W, Fr *G, Fr *GI, Fr *consts, unsigned log_n) {
+    size_t n = (size_t)1 << log_n;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr w = fr_root_of_unity();
+    for (unsigned k = log_n; k < 32; k++) w = w * w;
+    Fr g = fr_generator();
+    Fr minv = fr_pow_u64(fr_inv2(), log_n);      // (2^log_n)^-1
+    store_fr(W + i, fr_pow_u64(w, i));
+    store_fr(G + i, fr_pow_u64(g, i));
+    store_fr(GI + i, fr_pow_u64(fr_generator_inv(), i) * minv);
+    if (i == 0) {
+        store_fr(consts, minv);
+        store_fr(consts + 1, (fr_pow_u64(g, n) - Fr::one()).inverse());   // divide_by_z_on_coset: (g^m - 1)^-1
+    }
+}
+
+__device__ __forceinline__ unsigned bitrev(unsigned x, int bits) { return bits ? (__brev(x) >> (32 - bits)) : 0; }
+
+// In-place decimation-in-frequency transform of `cnt` independent tiles of 2^lb points held in
+// shared memory (tile t at sm + t * 2^lb).  Twiddle for the butterfly (i, i+h) of a 2h-group is
+// w_N^(j * N/(2h)), j = i mod h; inverse transforms index the table from the other end.
+__device__ __forceinline__ void smem_dif(Fr *sm, int lb, int cnt, const Fr *__restrict__ W, unsigned log_n, bool inverse) {
+    const unsigned n_mask = (1u << log_n) - 1;
+    const int half_total = (cnt << lb) >> 1;
+    for (int s = lb - 1; s >= 0; s--) {
+        const int h = 1 << s;
+        __syncthreads();
+        for (int q = threadIdx.x; q < half_total; q += NTT_THREADS) {
+            int j = q & (h - 1);
+            int i = ((q >> s) << (s + 1)) | j;          // covers all tiles: tile size is a multiple of 2h
+            Fr a = sm[i], b = sm[i + h];
+            unsigned e = (unsigned)j << (log_n - s - 1);
+            if (inverse) e = (0u - e) & n_mask;
+            Fr d = a - b;
+            sm[i] = a + b;
+            sm[i + h] = s == 0 ? d : d * load_fr(W + e);   // j == 0 when h == 1: twiddle 1
+        }
+    }
+    __syncthreads();
+}
+
+// pass A: columns.  data viewed as [N1][N2]; block handles `cols` adjacent columns.
+__global__ void __launch_bounds__(NTT_THREADS) k_ntt_cols(Fr *__restrict__ data, unsigned log_n, int l1, int cols_log,
+                                                          const Fr *__restrict__ W, const Fr *__restrict__ G, int coset_in, int inverse) {
+    extern __shared__ unsigned char smraw[];
+    Fr *sm = reinterpret_cast<Fr *>(smraw);
+    const int l2 = log_n - l1, N1 = 1 << l1, cols = 1 << cols_log;
+    const size_t N2 = (size_t)1 << l2;
+    Fr *x = data + ((size_t)blockIdx.y << log_n);
+    const size_t c0 = (size_t)blockIdx.x << cols_log;
+    const int total = N1 << cols_log;
+    const unsigned n_mask = (1u << log_n) - 1;
+    // load: consecutive threads take consecutive columns of one row (cols*32 B contiguous); tile layout [col][n1]
+    for (int q = threadIdx.x; q < total; q += NTT_THREADS) {
+        int col = q & (cols - 1), n1 = q >> cols_log;
+        size_t idx = (size_t)n1 * N2 + c0 + col;
+        Fr v = load_fr(x + idx);
+        if (coset_in) v = v * load_fr(G + idx);
+        sm[(col << l1) + n1] = v;
+    }
+    smem_dif(sm, l1, cols, W, log_n, inverse != 0);
+    // store: frequency m1 sits at position bitrev(m1); multiply by the four-step twiddle w^(n2*m1)
+    for (int q = threadIdx.x; q < total; q += NTT_THREADS) {
+        int col = q & (cols - 1), m1 = q >> cols_log;
+        size_t n2 = c0 + col;
+        Fr v = sm[(col << l1) + bitrev(m1, l1)];
+        unsigned e = (unsigned)((n2 * (size_t)m1) & n_mask);
+        if (inverse) e = (0u - e) & n_mask;
+        if (e) v = v * load_fr(W + e);
+        store_fr(x + (size_t)m1 * N2 + n2, v);
+    }
+}
+
+// pass B: rows.  in viewed as [N1][N2]; block handles `rows` adjacent rows; out[m1 + N1*m2].
+// post: 0 none, 1 multiply by consts[0] (m^-1), 2 multiply by GI[out index] (g^-i m^-1)
+__global__ void __launch_bounds__(NTT_THREADS) k_ntt_rows(const Fr *__restrict__ in, Fr *__restrict__ out, unsigned log_n, int l1, int rows_log,
+                                                          const Fr *__restrict__ W, const Fr *__restrict__ G, const Fr *__restrict__ GI,
+                                                          const Fr *__restrict__ consts, int coset_in, int inverse, int post) {
+    extern __shared__ unsigned char smraw[];
+    Fr *sm = reinterpret_cast<Fr *>(smraw);
+    const int l2 = log_n - l1, N2 = 1 << l2, rows = 1 << rows_log;
+    const size_t N1 = (size_t)1 << l1;
+    const Fr *x = in + ((size_t)blockIdx.y << log_n);
+    Fr *y = out + ((size_t)blockIdx.y << log_n);
+    const size_t r0 = (size_t)blockIdx.x << rows_log;
+    const int total = N2 << rows_log;
+    for (int q = threadIdx.x; q < total; q += NTT_THREADS) {     // rows are contiguous: fully coalesced
+        size_t idx = (r0 << l2) + q;
+        Fr v = load_fr(x + idx);
+        if (coset_in) v = v * load_fr(G + idx);                    // only when there is no pass A (l1 == 0)
+        sm[q] = v;
+    }
+    smem_dif(sm, l2, rows, W, log_n, inverse != 0);
+    Fr scale = Fr::one();
+    if (post == 1) scale = load_fr(consts);
+    for (int q = threadIdx.x; q < total; q += NTT_THREADS) {     // consecutive threads: consecutive m1 of one m2
+        int row = q & (rows - 1), m2 = q >> rows_log;
+        Fr v = sm[(row << l2) + bitrev(m2, l2)];
+        size_t o = (r0 + row) + N1 * (size_t)m2;
+        if (post == 1) v = v * scale;
+        else if (post == 2) v = v * load_fr(GI + o);
+        store_fr(y + o, v);
+    }
+}
+
+}  // namespace
+
+struct NttTables { unsigned log_n = 0; bool valid = false; DevBuf w, g, gi, consts; };
+static NttTables g_tables[8][6];   // [device][slot]
+
+static int get_tables(zk_ctx *ctx, unsigned log_n, NttTables **out) {
+    if (ctx->device >= 8) { zk_set_error("device index too large"); return ZK_ERR_INVALID; }
+    NttTables *slots = g_tables[ctx->device], *free_slot = nullptr;
+    for (int i = 0; i < 6; i++) {
+        if (slots[i].valid && slots[i].log_n == log_n) { *out = &slots[i]; return ZK_OK; }
+        if (!slots[i].valid && !free_slot) free_slot = &slots[i];
+    }
+    if (!free_slot) free_slot = &slots[log_n % 6];
+    size_t n = (size_t)1 << log_n;
+    ZK_TRY(free_slot->w.reserve(n * 32)); ZK_TRY(free_slot->g.reserve(n * 32)); ZK_TRY(free_slot->gi.reserve(n * 32)); ZK_TRY(free_slot->consts.reserve(64));
+    k_ntt_tables<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(free_slot->w.as<Fr>(), free_slot->g.as<Fr>(), free_slot->gi.as<Fr>(),
+                                                                       free_slot->consts.as<Fr>(), log_n);
+    ZK_CUDA(cudaGetLastError());
+    free_slot->log_n = log_n; free_slot->valid = true;
+    *out = free_slot;
+    return ZK_OK;
+}
+
+// `batch` transforms of 2^log_n contiguous elements each, in place in d_data.
+int zk_ntt_run(zk_ctx *ctx, void *d_data, unsigned log_n, int mode, size_t batch) {
+    if (log_n > 32) { zk_set_error("PolynomialDegreeTooLarge: log_n = %u", log_n); return ZK_ERR_POLY_DEGREE_TOO_LARGE; }
+    if (log_n > 2 * MAX_TILE_LOG) { zk_set_error("NTT sizes above 2^%d are not implemented", 2 * MAX_TILE_LOG); return ZK_ERR_INVALID; }
+    if (mode < 0 || mode > 3 || batch == 0 || batch > 65535) { zk_set_error("zk_ntt: bad mode/batch"); return ZK_ERR_INVALID; }
+    ZK_TRY(zk_use_device(ctx));
+    if (log_n == 0) return ZK_OK;     // size-1 transform is the identity (m^-1 = 1)
+    NttTables *t;
+    ZK_TRY(get_tables(ctx, log_n, &t));
+    const size_t n = (size_t)1 << log_n;
+    ZK_TRY(ctx->ntt_tmp.reserve(n * 32 * batch));
+    const int inverse = (mode == ZK_NTT_IFFT || mode == ZK_NTT_ICOSET_FFT);
+    const int coset_in = (mode == ZK_NTT_COSET_FFT);
+    const int post = mode == ZK_NTT_IFFT ? 1 : (mode == ZK_NTT_ICOSET_FFT ? 2 : 0);
+    const int l1 = log_n > MAX_TILE_LOG ? (int)log_n / 2 : 0, l2 = (int)log_n - l1;
+    static bool attr_done = false;
+    if (!attr_done) {
+        ZK_CUDA(cudaFuncSetAttribute(k_ntt_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << MAX_TILE_LOG));
+        ZK_CUDA(cudaFuncSetAttribute(k_ntt_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << MAX_TILE_LOG));
+        attr_done = true;
+    }
+    Fr *data = (Fr *)d_data, *tmp = ctx->ntt_tmp.as<Fr>();
+    if (l1 > 0) {
+        int cols_log = MAX_TILE_LOG - l1; if (cols_log > l2) cols_log = l2;
+        dim3 g((unsigned)(n >> (l1 + cols_log)), (unsigned)batch);
+        k_ntt_cols<<<g, NTT_THREADS, (size_t)32 << (l1 + cols_log), ctx->stream>>>(data, log_n, l1, cols_log, t->w.as<Fr>(), t->g.as<Fr>(), coset_in, inverse);
+    }
+    int rows_log = MAX_TILE_LOG - l2; if (rows_log > l1) rows_log = l1;
+    dim3 g((unsigned)(n >> (l2 + rows_log)), (unsigned)batch);
+    k_ntt_rows<<<g, NTT_THREADS, (size_t)32 << (l2 + rows_log), ctx->stream>>>(data, tmp, log_n, l1, rows_log, t->w.as<Fr>(), t->g.as<Fr>(), t->gi.as<Fr>(),
+                                                                             t->consts.as<Fr>(), l1 == 0 ? coset_in : 0, inverse, post);
+    ZK_CUDA(cudaGetLastError());
+    ZK_CUDA(cudaMemcpyAsync(data, tmp, n * 32 * batch, cudaMemcpyDeviceToDevice, ctx->stream));
+    return ZK_OK;
+}
+
+extern "C" int zk_ntt_fr_device(zk_ctx *ctx, void *d_data, unsigned log_n, int mode) {
+    if (!ctx || !d_data) { zk_set_error("zk_ntt_fr_device: NULL argument"); return ZK_ERR_INVALID; }
+    return zk_ntt_run(ctx, d_data, log_n, mode, 1);
+}
+extern "C" int zk_ntt_fr(zk_ctx *ctx, uint64_t *data, unsigned log_n, int mode) {
+    if (!ctx || !data) { zk_set_error("zk_ntt_fr: NULL argument"); return ZK_ERR_INVALID; }
+    if (log_n > 32) { zk_set_error("PolynomialDegreeTooLarge: log_n = %u", log_n); return ZK_ERR_POLY_DEGREE_TOO_LARGE; }
+    ZK_TRY(zk_use_device(ctx));
+    size_t bytes = ((size_t)1 << log_n) * 32;
+    ZK_TRY(ctx->stage_a.reserve(bytes));
+    ZK_CUDA(cudaMemcpyAsync(ctx->stage_a.p, data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ZK_TRY(zk_ntt_run(ctx, ctx->stage_a.p, log_n, mode, 1));
+    ZK_CUDA(cudaMemcpyAsync(data, ctx->stage_a.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZK_OK;
+}
+
+// ---- element-wise Fr kernels of create_proof ------------------------------------------
+namespace {
+// evals: [batch][n_c] canonical -> dst[batch][which][m] Montgomery, zero padded (EvaluationDomain::from_coeffs)
+__global__ void k_load_evals(const Fr *__restrict__ src, size_t n_c, unsigned log_m, int which, Fr *__restrict__ dst, int *err) {
+    size_t m = (size_t)1 << log_m;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t b = blockIdx.y;
+    if (i >= m) return;
+    Fr v = Fr::zero();
+    if (i < n_c) {
+        Fr c = load_fr(src + b * n_c + i);
+        if (!Fr::canonical_lt_mod(c)) atomicExch(err, 1);
+        v = Fr::from_canonical(c);
+    }
+    store_fr(dst + ((b * 3 + which) << log_m) + i, v);
+}
+// h[b][i] = (a*b - c) * zinv   over the coset evaluations (mul_assign, sub_assign, divide_by_z_on_coset)
+__global__ void k_quotient(const Fr *__restrict__ abc, unsigned log_m, const Fr *__restrict__ consts, Fr *__restrict__ h) {
+    size_t m = (size_t)1 << log_m;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t b = blockIdx.y;
+    if (i >= m) return;
+    const Fr *base = abc + ((b * 3) << log_m);
+    Fr a = load_fr(base + i), bb = load_fr(base + m + i), c = load_fr(base + 2 * m + i);
+    store_fr(h + (b << log_m) + i, (a * bb - c) * load_fr(consts + 1));
+}
+// scal[b][i] = into_repr(h[b][i]), i < n_out; scal[b][n_out .. n_total) left for the caller (extra terms)
+__global__ void k_into_repr(const Fr *__restrict__ h, unsigned log_m, size_t n_out, size_t n_total, Fr *__restrict__ scal) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t b = blockIdx.y;
+    if (i >= n_out) return;
+    store_fr(scal + b * n_total + i, load_fr(h + (b << log_m) + i).to_canonical());
+}
+// per proof: out[b][0] = 1, out[b][1] = r, out[b][2] = s, out[b][3] = -(r*s)  (all canonical) — the extra MSM terms
+__global__ void k_blinding_terms(const Fr *__restrict__ r, const Fr *__restrict__ s, size_t batch, Fr *__restrict__ out, int *err) {
+    size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    Fr rc = load_fr(r + b), sc = load_fr(s + b);
+    if (!Fr::canonical_lt_mod(rc) || !Fr::canonical_lt_mod(sc)) atomicExch(err, 1);
+    Fr one = Fr::zero(); one.l[0] = 1;
+    Fr rs = (Fr::from_canonical(rc) * Fr::from_canonical(sc)).neg().to_canonical();
+    store_fr(out + b * 4, one); store_fr(out + b * 4 + 1, rc); store_fr(out + b * 4 + 2, sc); store_fr(out + b * 4 + 3, rs);
+}
+}  // namespace
+
+int zk_fr_load_evals(zk_ctx *ctx, const void *d_src, size_t n_c, unsigned log_m, int which, size_t batch, void *d_dst) {
+    size_t m = (size_t)1 << log_m;
+    k_load_evals<<<dim3((unsigned)((m + 255) / 256), (unsigned)batch), 256, 0, ctx->stream>>>((const Fr *)d_src, n_c, log_m, which, (Fr *)d_dst, ctx->d_err);
+    ZK_CUDA(cudaGetLastError());
+    return ZK_OK;
+}
+int zk_fr_quotient(zk_ctx *ctx, const void *d_abc, unsigned log_m, size_t batch, void *d_h) {
+    NttTables *t;
+    ZK_TRY(get_tables(ctx, log_m, &t));
+    size_t m = (size_t)1 << log_m;
+    k_quotient<<<dim3((unsigned)((m + 255) / 256), (unsigned)batch), 256, 0, ctx->stream>>>((const Fr *)d_abc, log_m, t->consts.as<Fr>(), (Fr *)d_h);
+    ZK_CUDA(cudaGetLastError());
+    return ZK_OK;
+}
+int zk_fr_into_repr(zk_ctx *ctx, const void *d_h, unsigned log_m, size_t n_out, size_t n_total, size_t batch, void *d_scal) {
+    k_into_repr<<<dim3((unsigned)((n_out + 255) / 256), (unsigned)batch), 256, 0, ctx->stream>>>((const Fr *)d_h, log_m, n_out, n_total, (Fr *)d_scal);
+    ZK_CUDA(cudaGetLastError());
+    return ZK_OK;
+}
+int zk_fr_blinding_terms(zk_ctx *ctx, const void *d_r, const void *d_s, size_t batch, void *d_out) {
+    k_blinding_terms<<<(unsigned)((batch + 63) / 64), 64, 0, ctx->stream>>>((const Fr *)d_r, (const Fr *)d_s, batch, (Fr *)d_out, ctx->d_err);
+    ZK_CUDA(cudaGetLastError());
+    return ZK_OK;
+}

@@ -68,6 +68,15 @@ class Context:
     def sync(self):
         _ck(_lib.lib().zk_ctx_sync(self._h))
 
+    def profile(self, enable: bool):
+        _ck(_lib.lib().zk_ctx_profile(self._h, int(enable)))
+
+    def profile_read(self):
+        """(total ms, launches) of the dominant kernel since profile(True), CUDA events on this stream."""
+        ms, n = C.c_double(), C.c_uint64()
+        _ck(_lib.lib().zk_ctx_profile_read(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def close(self):
         if self._h:
             _lib.lib().zk_ctx_destroy(self._h)
@@ -110,6 +119,21 @@ def multiexp(bases: Bases, exponents) -> bytes:
     out = np.zeros(96 if bases.group == 1 else 192, np.uint8)
     _ck(_lib.lib().zk_msm(bases.ctx._h, bases._h, _p(e), e.shape[0], _p(out)))
     return out.tobytes()
+
+
+def multiexp_partial_device(bases: Bases, d_scalars_ptr: int, n: int, d_out_ptr: int):
+    """Partial MSM result (XYZZ point, zk_partial_size bytes) left in device memory for the NCCL all-gather."""
+    _ck(_lib.lib().zk_msm_partial_device(bases.ctx._h, bases._h, C.c_void_p(d_scalars_ptr), n, C.c_void_p(d_out_ptr)))
+
+
+def points_fold(ctx: Context, group: int, d_partials_ptr: int, count: int) -> bytes:
+    out = np.zeros(96 if group == 1 else 192, np.uint8)
+    _ck(_lib.lib().zk_points_fold(ctx._h, group, C.c_void_p(d_partials_ptr), count, _p(out)))
+    return out.tobytes()
+
+
+def partial_size(group: int) -> int:
+    return _lib.lib().zk_partial_size(group)
 
 
 def multiexp_device(bases: Bases, d_scalars_ptr: int, n: int, batch: int = 1) -> bytes:
