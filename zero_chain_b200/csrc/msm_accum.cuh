@@ -19,8 +19,9 @@ __device__ __forceinline__ Affine<F> load_affine(const Affine<F> *__restrict__ p
     for (int k = 0; k < (int)(sizeof(Affine<F>) / 16); k++) d[k] = __ldg(s + k);
     return r;
 }
-template <class F>
-__global__ void __launch_bounds__(128) k_accumulate(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ sorted,
+// MINB = minimum resident blocks per SM (register budget: 2 -> <=255 regs, 3 -> 168, 4 -> 128)
+template <class F, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_accumulate(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ sorted,
                                                     const uint32_t *__restrict__ bucket_off, const uint32_t *__restrict__ task_off,
                                                     uint32_t n_buckets, XYZZ<F> *__restrict__ partials) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;

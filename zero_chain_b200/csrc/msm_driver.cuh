@@ -4,6 +4,7 @@
 #include "internal.h"
 #include "msm.cuh"
 #include "codec.cuh"
+#include <stdlib.h>
 
 namespace zkmsm {
 
@@ -70,8 +71,16 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
     XYZZ<F> *partials = ctx->partials.as<XYZZ<F>>(), *buckets = ctx->buckets.as<XYZZ<F>>();
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (ctx->prof_on) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, st); }
-    k_accumulate<F><<<(unsigned)((t_max + 127) / 128), 128, 0, st>>>((const Affine<F> *)b->d_tbl, ctx->sorted.as<uint32_t>(),
-                                                                     ctx->bucket_off.as<uint32_t>(), ctx->task_off.as<uint32_t>(), (uint32_t)NB, partials);
+    {
+        static int minb = -1;          // experiment knob: ZK_ACC_MINB=2|3|4 (default chosen from measurements)
+        if (minb < 0) { const char *e = getenv("ZK_ACC_MINB"); minb = e ? atoi(e) : 2; }
+        const Affine<F> *tb = (const Affine<F> *)b->d_tbl;
+        const uint32_t *so = ctx->sorted.as<uint32_t>(), *bo = ctx->bucket_off.as<uint32_t>(), *to = ctx->task_off.as<uint32_t>();
+        unsigned grid = (unsigned)((t_max + 127) / 128);
+        if (minb == 3) k_accumulate<F, 3><<<grid, 128, 0, st>>>(tb, so, bo, to, (uint32_t)NB, partials);
+        else if (minb == 4) k_accumulate<F, 4><<<grid, 128, 0, st>>>(tb, so, bo, to, (uint32_t)NB, partials);
+        else k_accumulate<F, 2><<<grid, 128, 0, st>>>(tb, so, bo, to, (uint32_t)NB, partials);
+    }
     if (ctx->prof_on) { cudaEventRecord(ev1, st); ctx->prof_events.push_back(ev0); ctx->prof_events.push_back(ev1); }
     const size_t sm_warp = 4 * 32 * pt;      // 4 warps x 32 points
     if (sm_warp > 48 * 1024) {
