@@ -280,7 +280,63 @@ def secondary_metrics(ctx, zk, sy, args):
     fr_peak, _ = zk.bench_modmul(ctx, zk.FIELD_FR, 148 * 4, 256, 3000)
     out["ntt_fr_2^22"] = {"ms": ms, "melem_per_s": (1 << logn) / ms / 1e3, "algo_modmul_frac": (1 << (logn - 1)) * logn / (ms * 1e-3) / fr_peak,
                           "fr_modmul_peak": fr_peak}
+    out["groth16"] = prove_metrics(ctx, zk, sy, args)
     return out
+
+
+def prove_metrics(ctx, zk, sy, args, batch=256, steps=3):
+    """proofs/sec for the confidential_transfer-shaped synthetic circuit: batch of 256 witnesses in
+    pinned host memory -> zk_groth16_prove_batch (one C-ABI call per step, H2D of every witness and D2H of the proofs
+    inside the timed region); CPU: the oracle's create_proof on the same CRS and witness, all host threads."""
+    import torch
+    from oracle import coracle as co
+    r1cs = sy.make_r1cs(seed=1, **sy.CONF_SHAPE)
+    dens = sy.densities(r1cs)
+    g1 = lambda s: zk.scalar_mul_many(ctx, 1, zk.G1_GENERATOR, s)
+    g2 = lambda s: zk.scalar_mul_many(ctx, 2, zk.G2_GENERATOR, s)
+    crs = sy.make_toy_crs(r1cs, g1, g2, seed=2)                      # toy CRS (known trapdoor), exact Parameters::write bytes
+    t = time.time()
+    params = zk.Parameters.read(ctx, crs.params_bytes, checked=True)
+    load_s = time.time() - t
+    n_w = 8                                                          # distinct witnesses, cycled with distinct (r, s)
+    ws = []
+    for k in range(n_w):
+        z = sy.make_witness(r1cs, 100 + k)
+        a, b, c = sy.evaluate(r1cs, z)
+        ws.append([sy.ints_to_limbs(v) for v in (a, b, c, z[:r1cs.n_inputs], z[r1cs.n_inputs:])])
+    def pinned(j):
+        arr = np.stack([ws[k % n_w][j] for k in range(batch)])
+        return torch.from_numpy(arr.view(np.int64)).pin_memory()
+    bufs = [pinned(j) for j in range(5)]
+    views = [t_.numpy().view(np.uint64) for t_ in bufs]
+    rng = sy.SplitMix64(4242)
+    rs = sy.ints_to_limbs([rng.fr() for _ in range(batch)]); ss = sy.ints_to_limbs([rng.fr() for _ in range(batch)])
+    h2d = sum(v.nbytes for v in views) + rs.nbytes + ss.nbytes
+    zk.create_proof_batch_raw(params, batch, *views, *dens, rs, ss)          # warm-up (allocations, NTT tables)
+    zk.create_proof_batch_raw(params, batch, *views, *dens, rs, ss)
+    t = time.perf_counter()
+    for _ in range(steps):
+        proofs = zk.create_proof_batch_raw(params, batch, *views, *dens, rs, ss)
+    dt = (time.perf_counter() - t) / steps
+    t = time.perf_counter()
+    single = zk.create_proof_batch_raw(params, 1, *[v[:1] for v in views], *dens, rs[:1], ss[:1])
+    lat = time.perf_counter() - t
+    assert single == proofs[:192]
+    # CPU port of the reference path on the same CRS / witness
+    op = co.Params(crs.params_bytes, checked=False)
+    r0 = sum(int(x) << (64 * i) for i, x in enumerate(rs[0])); s0 = sum(int(x) << (64 * i) for i, x in enumerate(ss[0]))
+    w0 = [v[0] for v in views]
+    t = time.perf_counter(); want = op.prove(*w0, *dens, r0, s0); cpu_dt = time.perf_counter() - t
+    t = time.perf_counter(); op.prove(*w0, *dens, r0, s0); cpu_dt = min(cpu_dt, time.perf_counter() - t)
+    if want != proofs[:192]:
+        raise SystemExit("PARITY FAILURE: GPU proof bytes differ from the oracle")
+    params.free()
+    return {"metric": "proofs_per_sec (confidential_transfer shape: 19974 constraints, 23 inputs, domain 2^15; synthetic R1CS, toy CRS)",
+            "e2e_proofs_per_sec": batch / dt, "batch": batch, "steps": steps, "ms_per_batch": dt * 1e3, "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": 192 * batch, "single_proof_latency_ms": lat * 1e3, "params_load_checked_s": load_s,
+            "cpu_baseline": {"value": 1.0 / cpu_dt, "unit": "proofs/s", "cores": co.num_threads(), "kind": "port",
+                             "sample": "oracle create_proof, best of 2, same CRS/witness", "matches_gpu_proof_bytes": True},
+            "timing": "host wall clock around synchronous C-ABI calls (each call ends with a stream synchronise)"}
 
 
 def run_reference(args):

@@ -143,3 +143,27 @@ def test_msm_batch_matches_single(ctx):
     for k in range(batch):
         assert got[96 * k:96 * k + 96] == _enc(1, co.g1_msm(bases, scal[k]))
     b.free()
+
+
+def test_msm_2_20_closed_form_full_size(ctx):
+    """BASELINE config size (2^20 terms), checked without the oracle's O(n) curve work: bases P_i = (i+1)*G
+    (the construction of the reference's vector files) give  sum s_i P_i = (sum s_i (i+1) mod r) * G."""
+    n = 1 << 20
+    idx = np.zeros((n, 4), np.uint64); idx[:, 0] = np.arange(1, n + 1, dtype=np.uint64)
+    bases = zk.scalar_mul_many(ctx, 1, zk.G1_GENERATOR, idx)
+    assert np.array_equal(bases[:3], co.g1_fixed_base(idx[:3])) and np.array_equal(bases[-1], co.g1_fixed_base(idx[-1:])[0])
+    scal = sy.random_fr_limbs(n, 2020)
+    scal[:4] = co.ints_to_limbs([0, 1, pr.R - 1, 2], 4)
+    b = zk.Bases(ctx, 1, bases, window_bits=16, precompute=True)
+    got = zk.multiexp(b, scal)
+    s = scal.astype(object)
+    vals = s[:, 0] + (s[:, 1] << 64) + (s[:, 2] << 128) + (s[:, 3] << 192)
+    k = int(sum(int(v) * (i + 1) for i, v in enumerate(vals)) % pr.R)
+    assert got == pr.g1_uncompressed(pr.ec_mul(pr.FQ, pr.G1_GEN, k))
+    # linearity: MSM(s) + MSM(t) = MSM(s + t)
+    t = sy.random_fr_limbs(n, 2021)
+    tv = t.astype(object); tvals = tv[:, 0] + (tv[:, 1] << 64) + (tv[:, 2] << 128) + (tv[:, 3] << 192)
+    st = co.ints_to_limbs([(int(x) + int(y)) % pr.R for x, y in zip(vals, tvals)], 4)
+    p1 = pr.g1_from_uncompressed(got); p2 = pr.g1_from_uncompressed(zk.multiexp(b, t)); p3 = pr.g1_from_uncompressed(zk.multiexp(b, st))
+    assert pr.ec_add(pr.FQ, p1, p2) == p3
+    b.free()

@@ -118,19 +118,27 @@ static __global__ void __launch_bounds__(SORT_THREADS) k_scatter(const uint32_t 
 // ---- generic exclusive scan of u32 (three-phase; out[n] = total) -----------------------------------
 constexpr int SCAN_T = 256, SCAN_E = 8, SCAN_B = SCAN_T * SCAN_E;
 template <bool TASKS>
-__device__ __forceinline__ uint32_t scan_load(const uint32_t *in, size_t i) {
+__device__ __forceinline__ uint32_t scan_load(const uint32_t *in, size_t i, uint32_t task_len) {
     uint32_t v = in[i];
-    return TASKS ? (v + TASK_LEN - 1) / TASK_LEN : v;
+    return TASKS ? (v + task_len - 1) / task_len : v;
 }
-// TASKS: scan ceil(in/TASK_LEN) instead of in
+// task length from the number of non-zero entries (bucket_off[NB]): keeps ~TARGET_TASKS tasks in flight
+static __global__ void k_pick_task_len(const uint32_t *__restrict__ total_entries, uint32_t *__restrict__ task_len) {
+    uint32_t t = (*total_entries + TARGET_TASKS - 1) / TARGET_TASKS;
+    if (t < (uint32_t)TASK_LEN_MIN) t = TASK_LEN_MIN;
+    if (t > (uint32_t)TASK_LEN_MAX) t = TASK_LEN_MAX;
+    *task_len = t;
+}
+// TASKS: scan ceil(in / *task_len_p) instead of in
 template <bool TASKS>
 __global__ void __launch_bounds__(SCAN_T) k_scan_block(const uint32_t *__restrict__ in, uint32_t *__restrict__ out,
-                                                       uint32_t *__restrict__ block_sums, size_t n) {
+                                                       uint32_t *__restrict__ block_sums, size_t n, const uint32_t *__restrict__ task_len_p) {
     __shared__ uint32_t wsum[SCAN_T / 32];
+    const uint32_t task_len = TASKS ? *task_len_p : 1u;
     size_t base = (size_t)blockIdx.x * SCAN_B + (size_t)threadIdx.x * SCAN_E;
     uint32_t v[SCAN_E], s = 0;
 #pragma unroll
-    for (int k = 0; k < SCAN_E; k++) { v[k] = base + k < n ? scan_load<TASKS>(in, base + k) : 0; s += v[k]; }
+    for (int k = 0; k < SCAN_E; k++) { v[k] = base + k < n ? scan_load<TASKS>(in, base + k, task_len) : 0; s += v[k]; }
     uint32_t inc = s;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if ((threadIdx.x & 31) >= o) inc += t; }
@@ -153,14 +161,14 @@ static __global__ void k_scan_add(uint32_t *__restrict__ out, const uint32_t *__
     uint32_t o = block_off[blockIdx.x];
     for (int k = 0; k < SCAN_E; k++, i += SCAN_T) if (i < n) out[i] += o;
 }
-// out[0..n) = exclusive prefix sums of in (or of ceil(in/TASK_LEN) when TASKS), out[n] = total.
+// out[0..n) = exclusive prefix sums of in (or of ceil(in / *task_len_p) when TASKS), out[n] = total.
 // scratch must hold >= 2 * (n / SCAN_B + 8) words.
 template <bool TASKS>
-inline void exclusive_scan(const uint32_t *in, uint32_t *out, size_t n, uint32_t *scratch, cudaStream_t st) {
+inline void exclusive_scan(const uint32_t *in, uint32_t *out, size_t n, uint32_t *scratch, cudaStream_t st, const uint32_t *task_len_p = nullptr) {
     size_t nb = (n + SCAN_B - 1) / SCAN_B;
     if (nb == 0) nb = 1;
     uint32_t *bs = scratch;
-    k_scan_block<TASKS><<<(unsigned)nb, SCAN_T, 0, st>>>(in, out, bs, n);
+    k_scan_block<TASKS><<<(unsigned)nb, SCAN_T, 0, st>>>(in, out, bs, n, task_len_p);
     if (nb == 1) {
         cudaMemcpyAsync(out + n, bs, 4, cudaMemcpyDeviceToDevice, st);
         return;
@@ -237,10 +245,14 @@ __global__ void __launch_bounds__(RED_T) k_bit_sums(const XYZZ<F> *__restrict__ 
     if (gw >= (size_t)n_slices * n_bits * n_dom) return;
     int slice = (int)(gw % n_slices), bit = (int)((gw / n_slices) % n_bits), dom = (int)(gw / ((size_t)n_slices * n_bits));
     const XYZZ<F> *p = B + (size_t)dom * N;
-    int j0 = slice * RED_SLICE, j1 = j0 + RED_SLICE < N ? j0 + RED_SLICE : N;
+    // the k-th digit value d in [1, N] with bit `bit` set: d = ((k >> bit) << (bit + 1)) | 1 << bit | (k & (2^bit - 1)).
+    // Lanes stride over k, so there is no divergence on the bit test; a slice is RED_SLICE/2 consecutive k.
+    uint32_t k0 = (uint32_t)slice * (RED_SLICE / 2), k1 = k0 + RED_SLICE / 2;
     XYZZ<F> acc = XYZZ<F>::inf();
-    for (int j = j0 + (int)lane; j < j1; j += 32)
-        if (((uint32_t)(j + 1) >> bit) & 1u) acc.add(p[j]);
+    for (uint32_t k = k0 + lane; k < k1; k += 32) {
+        uint32_t d = ((k >> bit) << (bit + 1)) | (1u << bit) | (k & ((1u << bit) - 1u));
+        if (d <= (uint32_t)N) acc.add(p[d - 1]);
+    }
     warp_tree(slot, acc, lane);
     if (lane == 0) part[((size_t)dom * n_bits + bit) * n_slices + slice] = acc;
 }

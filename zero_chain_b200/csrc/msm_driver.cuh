@@ -29,7 +29,9 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
     if (E >= ((size_t)1 << 31)) { zk_set_error("MSM too large for 31-bit entry payloads (n*W*batch = %zu)", E); return ZK_ERR_INVALID; }
     const int tiles = (int)((e_dom + TILE - 1) / TILE);
     const size_t NB = n_dom * nbins;
-    const size_t t_max = E / TASK_LEN + NB + 1;
+    // tasks: ceil(size_b / task_len) summed over buckets <= total/task_len + NB, task_len = clamp(ceil(total/TARGET), MIN, MAX)
+    size_t t_max = E / TASK_LEN_MAX; if (t_max < 2 * (size_t)TARGET_TASKS) t_max = 2 * (size_t)TARGET_TASKS; if (t_max > E / TASK_LEN_MIN + 1) t_max = E / TASK_LEN_MIN + 1;
+    t_max += NB + 1;
     const size_t pt = sizeof(XYZZ<F>);
     ZK_TRY(ctx->digits.reserve(E * 4));
     ZK_TRY(ctx->tile_hist.reserve(n_dom * tiles * (size_t)nbins * 2));
@@ -42,7 +44,7 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
     ZK_TRY(ctx->partials.reserve(t_max * pt));
     ZK_TRY(ctx->buckets.reserve(NB * pt));
     const int n_bits = c;                      // digit values d in [1, 2^(c-1)] need c bits
-    const int n_slices = (nbins + RED_SLICE - 1) / RED_SLICE;
+    const int n_slices = (nbins / 2 + RED_SLICE / 2 - 1) / (RED_SLICE / 2) > 0 ? (nbins / 2 + RED_SLICE / 2 - 1) / (RED_SLICE / 2) : 1;   // slices of RED_SLICE/2 qualifying digit values
     ZK_TRY(ctx->red_part.reserve(n_dom * n_bits * (size_t)n_slices * pt));
     ZK_TRY(ctx->red_x.reserve(n_dom * n_bits * pt));
     ZK_TRY(ctx->result.reserve((n_dom + batch + 1) * pt));
@@ -63,7 +65,9 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
     k_col_scan<<<(unsigned)((NB + 255) / 256), 256, 0, st>>>(ctx->tile_hist.as<uint16_t>(), ctx->tile_off.as<uint32_t>(), ctx->sizes.as<uint32_t>(),
                                                             nbins, tiles, (int)n_dom);
     exclusive_scan<false>(ctx->sizes.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(), NB, ctx->scan_scratch.as<uint32_t>(), st);
-    exclusive_scan<true>(ctx->sizes.as<uint32_t>(), ctx->task_off.as<uint32_t>(), NB, ctx->scan_scratch.as<uint32_t>(), st);
+    uint32_t *d_task_len = (uint32_t *)(ctx->d_err + 8);
+    k_pick_task_len<<<1, 1, 0, st>>>(ctx->bucket_off.as<uint32_t>() + NB, d_task_len);
+    exclusive_scan<true>(ctx->sizes.as<uint32_t>(), ctx->task_off.as<uint32_t>(), NB, ctx->scan_scratch.as<uint32_t>(), st, d_task_len);
     k_scatter<<<gs, SORT_THREADS, smem, st>>>(digits, e_dom, nbins, ctx->tile_off.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(),
                                               ctx->sorted.as<uint32_t>(), tiles);
     // 3. accumulate + combine.  The payload of an entry is its position in the domain = [w][i] index;
@@ -73,13 +77,13 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
     if (ctx->prof_on) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, st); }
     {
         static int minb = -1;          // experiment knob: ZK_ACC_MINB=2|3|4 (default chosen from measurements)
-        if (minb < 0) { const char *e = getenv("ZK_ACC_MINB"); minb = e ? atoi(e) : 2; }
+        if (minb < 0) { const char *e = getenv("ZK_ACC_MINB"); minb = e ? atoi(e) : 3; }
         const Affine<F> *tb = (const Affine<F> *)b->d_tbl;
         const uint32_t *so = ctx->sorted.as<uint32_t>(), *bo = ctx->bucket_off.as<uint32_t>(), *to = ctx->task_off.as<uint32_t>();
         unsigned grid = (unsigned)((t_max + 127) / 128);
-        if (minb == 3) k_accumulate<F, 3><<<grid, 128, 0, st>>>(tb, so, bo, to, (uint32_t)NB, partials);
-        else if (minb == 4) k_accumulate<F, 4><<<grid, 128, 0, st>>>(tb, so, bo, to, (uint32_t)NB, partials);
-        else k_accumulate<F, 2><<<grid, 128, 0, st>>>(tb, so, bo, to, (uint32_t)NB, partials);
+        if (minb == 3) k_accumulate<F, 3><<<grid, 128, 0, st>>>(tb, so, bo, to, (uint32_t)NB, d_task_len, partials);
+        else if (minb == 4) k_accumulate<F, 4><<<grid, 128, 0, st>>>(tb, so, bo, to, (uint32_t)NB, d_task_len, partials);
+        else k_accumulate<F, 2><<<grid, 128, 0, st>>>(tb, so, bo, to, (uint32_t)NB, d_task_len, partials);
     }
     if (ctx->prof_on) { cudaEventRecord(ev1, st); ctx->prof_events.push_back(ev0); ctx->prof_events.push_back(ev1); }
     const size_t sm_warp = 4 * 32 * pt;      // 4 warps x 32 points

@@ -247,6 +247,18 @@ def create_proof_batch(provers, params: Parameters, rs, ss) -> bytes:
     return out.tobytes()
 
 
+def create_proof_batch_raw(params: Parameters, batch: int, a, b, c, inputs, aux, a_aux_density, b_input_density, b_aux_density, r, s) -> bytes:
+    """Same as create_proof_batch with the per-proof arrays already concatenated ([batch][n][4] uint64, e.g. views
+    of pinned host memory): exactly one zk_groth16_prove_batch call, no host-side copies."""
+    a, b, c, inputs, aux = (_u64(x, (batch, -1, 4)) for x in (a, b, c, inputs, aux))
+    r, s = _u64(r, (batch, 4)), _u64(s, (batch, 4))
+    d1, d2, d3 = (np.ascontiguousarray(x, np.uint8) for x in (a_aux_density, b_input_density, b_aux_density))
+    out = np.zeros(192 * batch, np.uint8)
+    _ck(_lib.lib().zk_groth16_prove_batch(params.ctx._h, params._h, batch, _p(a), _p(b), _p(c), a.shape[1],
+                                          _p(inputs), inputs.shape[1], _p(aux), aux.shape[1], _p(d1), _p(d2), _p(d3), _p(r), _p(s), _p(out)))
+    return out.tobytes()
+
+
 # ---- utilities ---------------------------------------------------------------------------------------
 def scalar_mul_many(ctx: Context, group: int, base_limbs, scalars):
     s = _u64(scalars, (-1, 4))
