@@ -23,6 +23,7 @@
 #include <stdint.h>
 #include "curve.cuh"
 #include "msm_accum.cuh"
+#include "tma.cuh"
 
 namespace zkmsm {
 
@@ -35,11 +36,22 @@ constexpr uint32_t DIGIT_ZERO = 0xffffffffu;
 // Signed digits d_w in (-2^(c-1), 2^(c-1)], sum d_w 2^(c w) = scalar.  Code: (|d|-1) | sign<<31, or DIGIT_ZERO.
 static __global__ void k_msm_digits(const uint32_t *__restrict__ scalars, uint32_t n, int c, int W,
                              uint32_t *__restrict__ digits, int *__restrict__ err) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    // stage this block's tile of scalars (blockDim.x * 32 B, contiguous) in shared memory with one bulk
+    // asynchronous copy (TMA engine, mbarrier completion), then every thread reads its own 32 bytes
+    __shared__ __align__(128) uint4 tile[256 * 2];
+    __shared__ uint64_t bar;
+    uint32_t i0 = blockIdx.x * blockDim.x, i = i0 + threadIdx.x;
     uint32_t ws = blockIdx.y;
+    uint32_t cnt = n - i0 < blockDim.x ? n - i0 : blockDim.x;
+    if (threadIdx.x == 0) zktma::mbar_init(&bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        zktma::mbar_expect_tx(&bar, cnt * 32u);
+        zktma::bulk_load(tile, scalars + ((size_t)ws * n + i0) * 8, cnt * 32u, &bar);
+    }
+    zktma::mbar_wait(&bar, 0);
     if (i >= n) return;
-    const uint4 *sp = reinterpret_cast<const uint4 *>(scalars + ((size_t)ws * n + i) * 8);
-    uint4 lo = sp[0], hi = sp[1];
+    uint4 lo = tile[2 * threadIdx.x], hi = tile[2 * threadIdx.x + 1];
     uint32_t k[9] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w, 0};
     {   // canonical check: k < r  (Fr::from_repr rejects otherwise, fr.rs:280-289)
         Fr t; for (int j = 0; j < 8; j++) t.l[j] = k[j];

@@ -19,6 +19,7 @@
 #define ZK_HOT 1
 #include "internal.h"
 #include "field.cuh"
+#include "tma.cuh"
 
 namespace {
 
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_cols(Fr *__restrict__ data,
 __global__ void __launch_bounds__(NTT_THREADS) k_ntt_rows(const Fr *__restrict__ in, Fr *__restrict__ out, unsigned log_n, int l1, int rows_log,
                                                           const Fr *__restrict__ W, const Fr *__restrict__ G, const Fr *__restrict__ GI,
                                                           const Fr *__restrict__ consts, int coset_in, int inverse, int post) {
-    extern __shared__ unsigned char smraw[];
+    extern __shared__ __align__(128) unsigned char smraw[];
     Fr *sm = reinterpret_cast<Fr *>(smraw);
     const int l2 = log_n - l1, N2 = 1 << l2, rows = 1 << rows_log;
     const size_t N1 = (size_t)1 << l1;
@@ -151,11 +152,24 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_rows(const Fr *__restrict__
     Fr *y = out + ((size_t)blockIdx.y << log_n);
     const size_t r0 = (size_t)blockIdx.x << rows_log;
     const int total = N2 << rows_log;
-    for (int q = threadIdx.x; q < total; q += NTT_THREADS) {     // rows are contiguous: fully coalesced
-        size_t idx = (r0 << l2) + q;
-        Fr v = load_fr(x + idx);
-        if (coset_in) v = v * load_fr(G + idx);                    // only when there is no pass A (l1 == 0)
-        sm[q] = v;
+    if (!coset_in) {
+        // the block's rows are one contiguous run of total*32 B: stage it with bulk asynchronous copies
+        // (TMA engine, mbarrier completion) instead of per-thread loads
+        __shared__ uint64_t bar;
+        const uint32_t bytes = (uint32_t)total * 32u, CH = 16384u;
+        if (threadIdx.x == 0) zktma::mbar_init(&bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            zktma::mbar_expect_tx(&bar, bytes);
+            const unsigned char *src = reinterpret_cast<const unsigned char *>(x + (r0 << l2));
+            for (uint32_t o = 0; o < bytes; o += CH) zktma::bulk_load(smraw + o, src + o, bytes - o < CH ? bytes - o : CH, &bar);
+        }
+        zktma::mbar_wait(&bar, 0);
+    } else {
+        for (int q = threadIdx.x; q < total; q += NTT_THREADS) {     // coset scaling on load (only when there is no pass A)
+            size_t idx = (r0 << l2) + q;
+            sm[q] = load_fr(x + idx) * load_fr(G + idx);
+        }
     }
     smem_dif(sm, l2, rows, W, log_n, inverse != 0);
     Fr scale = Fr::one();
