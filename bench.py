@@ -249,9 +249,16 @@ def run_ours(args):
             except Exception as e:      # the headline line must still print
                 line["secondary"] = {"error": repr(e)}
         print(json.dumps(line), flush=True)
+    # ordered teardown: tensors that were used on the library's stream must be released before the stream is
+    # destroyed with the context (their allocator blocks record events on it when freed)
+    del d_sets, pinned, d_stage, d_part, d_all
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    bases.free()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    ctx.close()
 
 
 def secondary_metrics(ctx, zk, sy, args):

@@ -282,14 +282,29 @@ __global__ void __launch_bounds__(RED_T) k_sum_points(const XYZZ<F> *__restrict_
     warp_tree(slot, acc, lane);
     if (lane == 0) out[g] = acc;
 }
+// one WARP per domain: R = sum_b 2^b X_b as a binary tree — at level s lane i (i % 2^(s+1) == 0) computes
+// X_i += 2^(2^s) * X_(i+2^s).  Serial depth 15 doublings + 4 additions instead of 15 + 15 for a Horner chain.
 template <class F>
-__global__ void k_finish_bits(const XYZZ<F> *__restrict__ X, int n_bits, int n_dom, XYZZ<F> *__restrict__ R) {
-    int dom = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(RED_T) k_finish_bits(const XYZZ<F> *__restrict__ X, int n_bits, int n_dom, XYZZ<F> *__restrict__ R) {
+    extern __shared__ unsigned char smraw[];
+    uint32_t lane = threadIdx.x & 31;
+    XYZZ<F> *slot = reinterpret_cast<XYZZ<F> *>(smraw) + (threadIdx.x >> 5) * 32;
+    int dom = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (dom >= n_dom) return;
-    const XYZZ<F> *x = X + (size_t)dom * n_bits;
-    XYZZ<F> r = x[n_bits - 1];
-    for (int b = n_bits - 2; b >= 0; b--) { r = r.dbl(); r.add(x[b]); }
-    R[dom] = r;
+    XYZZ<F> v = (int)lane < n_bits ? X[(size_t)dom * n_bits + lane] : XYZZ<F>::inf();
+    slot[lane] = v;
+    __syncwarp();
+    for (int s = 0; (1 << s) < n_bits; s++) {
+        int step = 1 << s;
+        if ((lane & (2 * step - 1)) == 0 && (int)lane + step < n_bits) {
+            XYZZ<F> hi = slot[lane + step];
+            for (int k = 0; k < step; k++) hi = hi.dbl();
+            v.add(hi);
+            slot[lane] = v;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) R[dom] = v;
 }
 // single thread: out = sum_w 2^(c w) R[w]  (Horner over windows; ad-hoc MSM without tables)
 template <class F>

@@ -26,7 +26,7 @@ template <class F, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_accumulate(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ sorted,
                                                     const uint32_t *__restrict__ bucket_off, const uint32_t *__restrict__ task_off,
                                                     uint32_t n_buckets, const uint32_t *__restrict__ task_len_p, XYZZ<F> *__restrict__ partials) {
-    const uint32_t TASK_LEN = *task_len_p;
+    (void)task_len_p;
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t n_tasks = task_off[n_buckets];
     if (t >= n_tasks) return;
@@ -34,8 +34,13 @@ __global__ void __launch_bounds__(128, MINB) k_accumulate(const Affine<F> *__res
     uint32_t lo = 0, hi = n_buckets;
     while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (task_off[mid] <= t) lo = mid; else hi = mid; }
     uint32_t b = lo, s = t - task_off[b];
-    uint32_t e0 = bucket_off[b] + s * TASK_LEN, e1 = bucket_off[b + 1];
-    if (e1 > e0 + TASK_LEN) e1 = e0 + TASK_LEN;
+    // split the bucket EVENLY over its tasks (all tasks of a bucket within one entry of each other), so the
+    // lanes of a warp run the same number of additions instead of full tasks next to a short remainder
+    uint32_t nt = task_off[b + 1] - task_off[b], b0 = bucket_off[b], size = bucket_off[b + 1] - b0;
+    uint32_t len = (size + nt - 1) / nt;
+    uint32_t e0 = b0 + s * len, e1 = e0 + len;
+    if (e1 > b0 + size) e1 = b0 + size;
+    if (e0 >= e1) { partials[t] = XYZZ<F>::inf(); return; }
     XYZZ<F> acc = XYZZ<F>::inf();
     uint32_t code = sorted[e0];
     Affine<F> nxt = load_affine(bases + (code & 0x7fffffffu));

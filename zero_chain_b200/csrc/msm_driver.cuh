@@ -91,6 +91,7 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
         ZK_CUDA(cudaFuncSetAttribute(k_combine_warp<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_warp));
         ZK_CUDA(cudaFuncSetAttribute(k_bit_sums<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_warp));
         ZK_CUDA(cudaFuncSetAttribute(k_sum_points<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_warp));
+        ZK_CUDA(cudaFuncSetAttribute(k_finish_bits<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_warp));
     }
     k_combine_serial<F><<<(unsigned)((NB + 127) / 128), 128, 0, st>>>(partials, ctx->task_off.as<uint32_t>(), (uint32_t)NB, buckets);
     k_combine_warp<F><<<(unsigned)((NB * 32 + 127) / 128), 128, sm_warp, st>>>(partials, ctx->task_off.as<uint32_t>(), (uint32_t)NB, buckets);
@@ -101,9 +102,9 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
     size_t n_g = n_dom * n_bits;
     k_sum_points<F><<<(unsigned)((n_g * 32 + RED_T - 1) / RED_T), RED_T, sm_warp, st>>>(part, n_slices, (int)n_g, X);
     if (tables) {
-        k_finish_bits<F><<<(unsigned)((n_dom + 31) / 32), 32, 0, st>>>(X, n_bits, (int)n_dom, R);
+        k_finish_bits<F><<<(unsigned)((n_dom * 32 + RED_T - 1) / RED_T), RED_T, sm_warp, st>>>(X, n_bits, (int)n_dom, R);
     } else {
-        k_finish_bits<F><<<(unsigned)((n_dom + 31) / 32), 32, 0, st>>>(X, n_bits, (int)n_dom, R + 1);
+        k_finish_bits<F><<<(unsigned)((n_dom * 32 + RED_T - 1) / RED_T), RED_T, sm_warp, st>>>(X, n_bits, (int)n_dom, R + 1);
         k_horner_windows<F><<<1, 32, 0, st>>>(R + 1, W, c, R);
     }
     ZK_CUDA(cudaGetLastError());
