@@ -425,3 +425,160 @@ class SplitMix64:
 
     def fq(self) -> int:
         return self.below(Q, 7)
+
+
+# ---------------------------------------------------------------------------------------
+# Pairing (verifier-side oracle).  Test infrastructure only, written for clarity:
+# Fq12 is represented as Fq[w]/(w^12 - 2 w^6 + 2) — the same field as the reference's tower
+# Fq2[v]/(v^3 - (u+1)), Fq6[w]/(w^2 - v) (fq6.rs, fq12.rs) because u = w^6 - 1 satisfies u^2 = -1.
+# The Miller loop uses the textbook affine formulas on E(Fq12) after untwisting Q; the final
+# exponentiation is the plain power (q^12 - 1)/r.  Pinned by the reference's fixture: conf_vk.dat[0:576]
+# = Fq12::write(e(alpha_g1, beta_g2)) (core/bellman-verifier/src/lib.rs:174-196, verifier.rs:15-30).
+BLS_X = 0xd201000000010000          # |x|; the BLS parameter is -x (mod.rs:23-25)
+
+
+def _f12_mul(a, b):
+    t = [0] * 23
+    for i, ai in enumerate(a):
+        if ai:
+            for j, bj in enumerate(b):
+                t[i + j] += ai * bj
+    for i in range(22, 11, -1):       # w^12 = 2 w^6 - 2
+        c = t[i]
+        if c:
+            t[i - 6] += 2 * c
+            t[i - 12] -= 2 * c
+    return [x % Q for x in t[:12]]
+
+
+def _f12_add(a, b): return [(x + y) % Q for x, y in zip(a, b)]
+def _f12_sub(a, b): return [(x - y) % Q for x, y in zip(a, b)]
+def _f12_scalar(a, k): return [x * k % Q for x in a]
+F12_ONE = [1] + [0] * 11
+F12_ZERO = [0] * 12
+
+
+def _poly_deg(p):
+    d = len(p) - 1
+    while d and p[d] == 0:
+        d -= 1
+    return d
+
+
+def _f12_inv(a):
+    """Extended Euclid on polynomials over Fq modulo w^12 - 2 w^6 + 2."""
+    lm, hm = [1] + [0] * 12, [0] * 13
+    low, high = list(a) + [0], [2, 0, 0, 0, 0, 0, (-2) % Q, 0, 0, 0, 0, 0, 1]
+    while _poly_deg(low):
+        dl, dh = _poly_deg(low), _poly_deg(high)
+        r = [0] * 13
+        tmp = list(high)
+        inv_lead = pow(low[dl], -1, Q)
+        for i in range(dh - dl, -1, -1):
+            r[i] = tmp[dl + i] * inv_lead % Q
+            for c in range(dl + 1):
+                tmp[c + i] = (tmp[c + i] - r[i] * low[c]) % Q
+        nm, new = list(hm), list(high)
+        for i in range(13):
+            for j in range(13 - i):
+                nm[i + j] = (nm[i + j] - lm[i] * r[j]) % Q
+                new[i + j] = (new[i + j] - low[i] * r[j]) % Q
+        lm, low, hm, high = nm, new, lm, low
+    c = pow(low[0], -1, Q)
+    return [x * c % Q for x in lm[:12]]
+
+
+def _f12_pow(a, e):
+    r, b = F12_ONE, a
+    while e:
+        if e & 1:
+            r = _f12_mul(r, b)
+        b = _f12_mul(b, b)
+        e >>= 1
+    return r
+
+
+def _fq2_to_f12(c):              # c0 + c1 u, u = w^6 - 1
+    r = [0] * 12
+    r[0] = (c[0] - c[1]) % Q
+    r[6] = c[1] % Q
+    return r
+
+
+def _untwist(q):
+    """E'(Fq2) -> E(Fq12): (x, y) -> (x / w^2, y / w^3)  (w^6 = 1 + u)."""
+    x, y = _fq2_to_f12(q[0]), _fq2_to_f12(q[1])
+    w2 = [0, 0, 1] + [0] * 9
+    w3 = [0, 0, 0, 1] + [0] * 8
+    return (_f12_mul(x, _f12_inv(w2)), _f12_mul(y, _f12_inv(w3)))
+
+
+def miller_loop(p, q):
+    """f_{|x|,Q}(P) conjugated for the negative BLS parameter; p in G1 (affine ints), q in G2 (affine Fq2 pairs)."""
+    if p is INF or q is INF:
+        return F12_ONE
+    xp = [p[0]] + [0] * 11
+    yp = [p[1]] + [0] * 11
+    Qx, Qy = _untwist(q)
+    Tx, Ty = Qx, Qy
+    f = F12_ONE
+
+    def line(lam, x1, y1):       # l(P) = (y_P - y_1) - lam (x_P - x_1)
+        return _f12_sub(_f12_sub(yp, y1), _f12_mul(lam, _f12_sub(xp, x1)))
+    for bit in bin(BLS_X)[3:]:
+        lam = _f12_mul(_f12_scalar(_f12_mul(Tx, Tx), 3), _f12_inv(_f12_scalar(Ty, 2)))
+        f = _f12_mul(_f12_mul(f, f), line(lam, Tx, Ty))
+        nx = _f12_sub(_f12_mul(lam, lam), _f12_scalar(Tx, 2))
+        Ty = _f12_sub(_f12_mul(lam, _f12_sub(Tx, nx)), Ty)
+        Tx = nx
+        if bit == "1":
+            lam = _f12_mul(_f12_sub(Qy, Ty), _f12_inv(_f12_sub(Qx, Tx)))
+            f = _f12_mul(f, line(lam, Tx, Ty))
+            nx = _f12_sub(_f12_sub(_f12_mul(lam, lam), Tx), Qx)
+            Ty = _f12_sub(_f12_mul(lam, _f12_sub(Tx, nx)), Ty)
+            Tx = nx
+    # x < 0: f_{x,Q} = 1 / f_{|x|,Q} up to factors killed by the final exponentiation; conjugation (w -> -w... the
+    # q^6-Frobenius) equals inversion on the cyclotomic subgroup, so invert here and let the exponentiation finish it.
+    return _f12_inv(f)
+
+
+def final_exponentiation(f):
+    return _f12_pow(f, (Q ** 12 - 1) // R)
+
+
+def pairing(p, q):
+    """Reduced pairing with the plain exponent (q^12 - 1)/r."""
+    return final_exponentiation(miller_loop(p, q))
+
+
+def pairing_reference(p, q):
+    """The value the reference's Engine::pairing returns: its final_exponentiation (mod.rs:104-160) uses the
+    x-addition chain of eprint 2016/130, which yields the CUBE of the plain reduced pairing.  Established against the
+    fixture conf_vk.dat[0:576] (tests/test_oracle_pairing.py); irrelevant for verification, where only == 1 matters."""
+    return _f12_pow(pairing(p, q), 3)
+
+
+def f12_to_tower_bytes(a) -> bytes:
+    """Fq12::write order (fq12.rs:29-45, fq6.rs:31-48, fq2.rs:40-44): for w^i (i=0,1), v^j (j=0..2), u^k (k=0,1): 48-byte BE."""
+    out = bytearray()
+    for i in range(2):
+        for j in range(3):
+            t = 2 * j + i
+            c1 = a[t + 6] % Q
+            c0 = (a[t] + a[t + 6]) % Q
+            out += c0.to_bytes(48, "big") + c1.to_bytes(48, "big")
+    return bytes(out)
+
+
+def groth16_verify(vk, proof_abc, public_inputs) -> bool:
+    """verify_proof (core/bellman-verifier/src/verifier.rs:32-63): e(A,B) = e(alpha,beta) e(sum x_i ic_i, gamma) e(C,delta).
+    vk: dict(alpha_g1, beta_g2, gamma_g2, delta_g2, ic=[...]) affine; public_inputs exclude the leading ONE."""
+    a, b, c = proof_abc
+    acc = vk["ic"][0]
+    for x, pt in zip(public_inputs, vk["ic"][1:]):
+        acc = ec_add(FQ, acc, ec_mul(FQ, pt, x))
+    m = miller_loop(a, b)
+    m = _f12_mul(m, miller_loop(ec_neg(FQ, vk["alpha_g1"]), vk["beta_g2"]))
+    m = _f12_mul(m, miller_loop(ec_neg(FQ, acc), vk["gamma_g2"]))
+    m = _f12_mul(m, miller_loop(ec_neg(FQ, c), vk["delta_g2"]))
+    return final_exponentiation(m) == F12_ONE

@@ -78,6 +78,13 @@ def main():
     for p in FILES:
         b = open(os.path.join(REF, p), "rb").read()
         res["files"][p] = {"size": len(b), "sha256": hashlib.sha256(b).hexdigest()}
+    # pairing known-answer: PreparedVerifyingKey.alpha_g1_beta_g2 = e(alpha_g1, beta_g2) as written by Fq12::write
+    # (core/bellman-verifier/src/lib.rs:174-196) at conf_vk.dat[0:576]; alpha_g1 / beta_g2 from conf_pk.dat's vk header
+    pk = open(os.path.join(REF, "zface/params/conf_pk.dat"), "rb").read()
+    vk = open(os.path.join(REF, "zface/params/conf_vk.dat"), "rb").read()
+    res["pairing_kat"] = {"alpha_g1_uncompressed": pk[0:96].hex(), "beta_g2_uncompressed": pk[192:384].hex(),
+                          "alpha_g1_beta_g2_fq12": vk[0:576].hex(),
+                          "source": "zface/params/conf_pk.dat[0:96], [192:384]; zface/params/conf_vk.dat[0:576]"}
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "kats.json")
     json.dump(res, open(out, "w"), indent=1)
     print("wrote", out, {k: len(v["groups"]) for k, v in res["tests"].items()})

@@ -119,3 +119,25 @@ def test_params_load_rejects(ctx):
         zk.create_proof(pa, params, 1, 2)
     assert e.value.code == -3
     params.free()
+
+
+def test_gpu_proof_verifies_by_pairing(ctx):
+    """The reference's own acceptance check for gen_proof (`check_proof` -> verify_proof, core/proofs/src/confidential.rs:
+    208-278): the GPU proof must satisfy e(A,B) = e(alpha,beta) e(sum x_i ic_i, gamma) e(C,delta) under the CRS's verifying
+    key.  The pairing is the big-integer oracle pinned by conf_vk.dat (tests/test_oracle_pairing.py)."""
+    from tests.test_oracle_pairing import proof_points, vk_from_params
+    r1cs = sy.make_r1cs(seed=8, **SHAPES["tiny"])
+    crs = sy.make_toy_crs(r1cs, co.g1_fixed_base, co.g2_fixed_base, seed=9)
+    params = zk.Parameters.read(ctx, crs.params_bytes, checked=True)
+    z, pa = _witness(r1cs, 3)
+    import random
+    proof = zk.create_random_proof(pa, params, random.Random(5))          # r, s drawn like create_random_proof
+    vk = vk_from_params(crs.params_bytes)
+    assert pr.groth16_verify(vk, proof_points(proof), z[1:r1cs.n_inputs])
+    bad = bytearray(proof); bad[100] ^= 4
+    try:
+        pts = proof_points(bytes(bad))
+        assert not pr.groth16_verify(vk, pts, z[1:r1cs.n_inputs])
+    except ValueError:
+        pass                                                              # not even a curve point any more
+    params.free()
