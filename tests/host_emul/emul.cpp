@@ -60,3 +60,36 @@ void emu_g2_add(const uint32_t *a, const uint32_t *b, uint32_t *o, int mixed) { 
 void emu_g1_mul(const uint32_t *a, const uint32_t *k, uint32_t *o) { t_mul<Fq>(a, k, o); }
 void emu_g2_mul(const uint32_t *a, const uint32_t *k, uint32_t *o) { t_mul<Fq2>(a, k, o); }
 }
+
+// ---- batched-affine pair additions (msm_affine.cuh): the per-pair classification / finish functions and the
+// simultaneous-inversion walk, replayed on the host for ONE bucket of n points -> ceil(n/2) points
+#include <vector>
+#include "msm_affine_core.cuh"
+template <class F> static void t_batch_pairs(const uint32_t *in, int n, uint32_t *out) {
+    using namespace zkmsm;
+    std::vector<Affine<F>> p(n);
+    memcpy(p.data(), in, sizeof(Affine<F>) * n);
+    int m = (n + 1) / 2;
+    std::vector<F> scratch(m);
+    std::vector<Affine<F>> o(m);
+    F run = F::one();
+    for (int j = 0; j < m; j++) {
+        bool has1 = 2 * j + 1 < n;
+        Affine<F> p0 = p[2 * j], p1 = has1 ? p[2 * j + 1] : Affine<F>::inf();
+        F den; pair_classify(p0, p1, has1, den);
+        scratch[j] = run; run = run * den;
+    }
+    F inv = run.inverse();
+    for (int j = m - 1; j >= 0; j--) {
+        bool has1 = 2 * j + 1 < n;
+        Affine<F> p0 = p[2 * j], p1 = has1 ? p[2 * j + 1] : Affine<F>::inf();
+        F den; int mode = pair_classify(p0, p1, has1, den);
+        F dinv = inv * scratch[j]; inv = inv * den;
+        o[j] = pair_finish(mode, p0, p1, dinv);
+    }
+    memcpy(out, o.data(), sizeof(Affine<F>) * m);
+}
+extern "C" {
+void emu_g1_batch_pairs(const uint32_t *in, int n, uint32_t *out) { t_batch_pairs<Fq>(in, n, out); }
+void emu_g2_batch_pairs(const uint32_t *in, int n, uint32_t *out) { t_batch_pairs<Fq2>(in, n, out); }
+}

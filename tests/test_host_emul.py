@@ -87,3 +87,20 @@ def test_curve_emulation(emu, g):
         kk = co.ints_to_limbs([k], 4)
         assert np.array_equal(_pt(emu, "emu_g%d_mul" % g, pts[4], kk, w), mul(pts[4], k))
     assert not np.any(_pt(emu, "emu_g%d_mul" % g, inf, co.ints_to_limbs([5], 4), w))
+
+
+@pytest.mark.parametrize("g", [1, 2])
+def test_batched_affine_pairs_emulation(emu, g):
+    """msm_affine_core.cuh: pairwise affine additions with ONE shared inversion, incl. the exceptional pairs
+    (P+P, P+(-P), infinity operand, odd leftover) — against the oracle's group law."""
+    w = 12 if g == 1 else 24
+    fixed = co.g1_fixed_base if g == 1 else co.g2_fixed_base
+    add = co.g1_add if g == 1 else co.g2_add
+    ks = [3, 5, 7, 7, 9, pr.R - 9, 0, 11, 13, 0, 0, 0, 21, 34, 55, 89, 144, 233, 377, 610, 17]      # odd count: leftover copied
+    pts = np.ascontiguousarray(fixed(co.ints_to_limbs(ks, 4)))
+    m = (len(ks) + 1) // 2
+    out = np.zeros((m, w), np.uint64)
+    getattr(emu, "emu_g%d_batch_pairs" % g)(pts.ctypes.data_as(C.c_void_p), len(ks), out.ctypes.data_as(C.c_void_p))
+    for j in range(m):
+        want = add(pts[2 * j], pts[2 * j + 1]) if 2 * j + 1 < len(ks) else pts[2 * j]
+        assert np.array_equal(out[j], want), j

@@ -27,7 +27,7 @@
 
 namespace zkmsm {
 
-constexpr int TILE = 32768;        // entries per sort tile (u16 tile counters)
+constexpr int TILE = 131072;       // entries per sort tile (one tile ~ one CTA of a single wave at 2^20 x 16 windows)
 constexpr int SORT_THREADS = 1024;
 constexpr uint32_t DIGIT_ZERO = 0xffffffffu;
 
@@ -77,7 +77,7 @@ static __global__ void k_msm_digits(const uint32_t *__restrict__ scalars, uint32
 
 // ---- 2. counting sort --------------------------------------------------------------------------
 static __global__ void __launch_bounds__(SORT_THREADS) k_tile_hist(const uint32_t *__restrict__ digits, uint64_t e_ws, int nbins,
-                                                            uint16_t *__restrict__ tile_hist, int tiles_per_ws) {
+                                                            uint32_t *__restrict__ tile_hist, int tiles_per_ws) {
     extern __shared__ uint32_t sh[];
     int tile = blockIdx.x, ws = blockIdx.y;
     for (int b = threadIdx.x; b < nbins; b += blockDim.x) sh[b] = 0;
@@ -89,11 +89,11 @@ static __global__ void __launch_bounds__(SORT_THREADS) k_tile_hist(const uint32_
         if (code != DIGIT_ZERO) atomicAdd(&sh[code & 0x7fffffffu], 1u);
     }
     __syncthreads();
-    uint16_t *o = tile_hist + ((size_t)ws * tiles_per_ws + tile) * nbins;
-    for (int b = threadIdx.x; b < nbins; b += blockDim.x) o[b] = (uint16_t)sh[b];
+    uint32_t *o = tile_hist + ((size_t)ws * tiles_per_ws + tile) * nbins;
+    for (int b = threadIdx.x; b < nbins; b += blockDim.x) o[b] = sh[b];
 }
 // thread per (ws, bin): exclusive prefix over tiles -> tile_off, total -> sizes
-static __global__ void k_col_scan(const uint16_t *__restrict__ tile_hist, uint32_t *__restrict__ tile_off, uint32_t *__restrict__ sizes,
+static __global__ void k_col_scan(const uint32_t *__restrict__ tile_hist, uint32_t *__restrict__ tile_off, uint32_t *__restrict__ sizes,
                            int nbins, int tiles_per_ws, int n_ws) {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= nbins * n_ws) return;

@@ -42,12 +42,13 @@ __global__ void __launch_bounds__(128, MINB) k_accumulate(const Affine<F> *__res
     if (e1 > b0 + size) e1 = b0 + size;
     if (e0 >= e1) { partials[t] = XYZZ<F>::inf(); return; }
     XYZZ<F> acc = XYZZ<F>::inf();
-    uint32_t code = sorted[e0];
+    // sorted == nullptr: the inputs are already-reduced affine points indexed by position (no sign)
+    uint32_t code = sorted ? sorted[e0] : e0;
     Affine<F> nxt = load_affine(bases + (code & 0x7fffffffu));
     for (uint32_t e = e0; e < e1; e++) {
         Affine<F> p = nxt;
         bool neg = code >> 31;
-        if (e + 1 < e1) { code = sorted[e + 1]; nxt = load_affine(bases + (code & 0x7fffffffu)); }
+        if (e + 1 < e1) { code = sorted ? sorted[e + 1] : e + 1; nxt = load_affine(bases + (code & 0x7fffffffu)); }
         p.y = p.y.cneg(neg);
         acc.add_mixed(p);
     }
