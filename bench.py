@@ -114,6 +114,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: stdout carries ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = 1 << args.log_n
     ctx = zk.Context(local)
@@ -138,8 +140,8 @@ def run_ours(args):
         if world == 1:
             return zk.multiexp_device(bases, d.data_ptr(), n)
         zk.multiexp_partial_device(bases, d.data_ptr(), n, d_part.data_ptr())
-        dist.all_gather_into_tensor(d_all, d_part)
-        torch.cuda.current_stream().synchronize()
+        with torch.cuda.stream(stream):                 # NCCL all-gather enqueued on the library's stream: no host sync needed
+            dist.all_gather_into_tensor(d_all, d_part)
         return zk.points_fold(ctx, 1, d_all.data_ptr(), world)
 
     d_stage = torch.empty_like(d_sets[0])
@@ -151,8 +153,8 @@ def run_ours(args):
         with torch.cuda.stream(stream):
             d_stage.copy_(h, non_blocking=True)
         zk.multiexp_partial_device(bases, d_stage.data_ptr(), n, d_part.data_ptr())
-        dist.all_gather_into_tensor(d_all, d_part)
-        torch.cuda.current_stream().synchronize()
+        with torch.cuda.stream(stream):
+            dist.all_gather_into_tensor(d_all, d_part)
         return zk.points_fold(ctx, 1, d_all.data_ptr(), world)
 
     def barrier():

@@ -93,3 +93,13 @@ extern "C" {
 void emu_g1_batch_pairs(const uint32_t *in, int n, uint32_t *out) { t_batch_pairs<Fq>(in, n, out); }
 void emu_g2_batch_pairs(const uint32_t *in, int n, uint32_t *out) { t_batch_pairs<Fq2>(in, n, out); }
 }
+
+#include "field_wide.cuh"
+extern "C" {
+void emu_fq_mul_sep(const uint32_t *a, const uint32_t *b, uint32_t *o) { Fq x, y; memcpy(x.l, a, 48); memcpy(y.l, b, 48); Fq r = zkwide::mul_sep(x, y); memcpy(o, r.l, 48); }
+void emu_fq_sqr_sep(const uint32_t *a, uint32_t *o) { Fq x; memcpy(x.l, a, 48); Fq r = zkwide::sqr_sep(x); memcpy(o, r.l, 48); }
+void emu_fq_mul_sub_mul(const uint32_t *a, const uint32_t *b, const uint32_t *c, const uint32_t *d, uint32_t *o) {
+    Fq x, y, z, w; memcpy(x.l, a, 48); memcpy(y.l, b, 48); memcpy(z.l, c, 48); memcpy(w.l, d, 48);
+    Fq r = zkwide::mul_sub_mul(x, y, z, w); memcpy(o, r.l, 48);
+}
+}

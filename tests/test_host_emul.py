@@ -104,3 +104,17 @@ def test_batched_affine_pairs_emulation(emu, g):
     for j in range(m):
         want = add(pts[2 * j], pts[2 * j + 1]) if 2 * j + 1 < len(ks) else pts[2 * j]
         assert np.array_equal(out[j], want), j
+
+
+def test_separated_multiply_reduce_emulation(emu):
+    """field_wide.cuh: column-wise product, dedicated squaring, shared reduction of a*b - c*d — all must equal the
+    interleaved Montgomery product's values (hence the reference's)."""
+    mod, n = pr.Q, 12
+    rinv = pow(1 << 384, -1, mod)
+    rng = pr.SplitMix64(77)
+    vals = [0, 1, mod - 1, mod - 2, (1 << 384) % mod, mod >> 1] + [rng.fq() for _ in range(600)]
+    for i in range(len(vals) - 3):
+        a, b, c, d = vals[i], vals[i + 1], vals[i + 2], vals[i + 3]
+        assert _call(emu, "emu_fq_mul_sep", n, a, b) == a * b * rinv % mod
+        assert _call(emu, "emu_fq_sqr_sep", n, a) == a * a * rinv % mod
+        assert _call(emu, "emu_fq_mul_sub_mul", n, a, b, c, d) == (a * b - c * d) * rinv % mod

@@ -2,6 +2,7 @@
 // inlined (ZK_HOT).  Everything else in the library calls them as functions (field.cuh, inlining policy).
 #define ZK_HOT 1
 #include "msm_driver.cuh"
+#include "field_wide.cuh"
 
 using namespace zkmsm;
 
@@ -23,7 +24,34 @@ __global__ void k_bench_modmul(int iters, T *sink) {
     T r = a[0] + a[1] + a[2] + a[3];
     if (r.l[0] == 0x12345678u && r.l[1] == 0x9abcdef0u) sink[0] = r;   // keep the work alive
 }
+// experiment: separated multiply / reduce (field_wide.cuh) against the interleaved product, 4 chains per thread
+template <int MODE>
+__global__ void k_bench_wide(int iters, Fq *sink) {
+    Fq a[4], b = Fq::one();
+    for (int k = 0; k < 4; k++) { a[k] = Fq::one(); a[k].l[0] += threadIdx.x + k + 1; }
+    b.l[1] ^= blockIdx.x + 7;
+    a[0] = Fq::reduce_once(a[0]); b = Fq::reduce_once(b);
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (MODE == 0) a[k] = a[k] * b;
+            else if (MODE == 1) a[k] = zkwide::mul_sep(a[k], b);
+            else if (MODE == 2) a[k] = a[k] * a[k];
+            else if (MODE == 3) a[k] = zkwide::sqr_sep(a[k]);
+            else if (MODE == 4) a[k] = a[k] * b - b * a[(k + 1) & 3];
+            else a[k] = zkwide::mul_sub_mul(a[k], b, b, a[(k + 1) & 3]);
+        }
+    }
+    Fq r = a[0] + a[1] + a[2] + a[3];
+    if (r.l[0] == 0x12345678u && r.l[1] == 0x9abcdef0u) sink[0] = r;
+}
 void zk_launch_bench_modmul(int field, int blocks, int threads, int iters, void *sink, cudaStream_t st) {
     if (field == 0) k_bench_modmul<Fq><<<blocks, threads, 0, st>>>(iters, (Fq *)sink);
-    else k_bench_modmul<Fr><<<blocks, threads, 0, st>>>(iters, (Fr *)sink);
+    else if (field == 1) k_bench_modmul<Fr><<<blocks, threads, 0, st>>>(iters, (Fr *)sink);
+    else if (field == 10) k_bench_wide<0><<<blocks, threads, 0, st>>>(iters, (Fq *)sink);
+    else if (field == 11) k_bench_wide<1><<<blocks, threads, 0, st>>>(iters, (Fq *)sink);
+    else if (field == 12) k_bench_wide<2><<<blocks, threads, 0, st>>>(iters, (Fq *)sink);
+    else if (field == 13) k_bench_wide<3><<<blocks, threads, 0, st>>>(iters, (Fq *)sink);
+    else if (field == 14) k_bench_wide<4><<<blocks, threads, 0, st>>>(iters, (Fq *)sink);
+    else k_bench_wide<5><<<blocks, threads, 0, st>>>(iters, (Fq *)sink);
 }
