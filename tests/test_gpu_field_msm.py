@@ -167,3 +167,45 @@ def test_msm_2_20_closed_form_full_size(ctx):
     p1 = pr.g1_from_uncompressed(got); p2 = pr.g1_from_uncompressed(zk.multiexp(b, t)); p3 = pr.g1_from_uncompressed(zk.multiexp(b, st))
     assert pr.ec_add(pr.FQ, p1, p2) == p3
     b.free()
+
+
+def test_partial_and_fold_single_process(ctx):
+    """The multi-GPU building blocks on one device: two shards' partial results (XYZZ points left in device memory,
+    as they would be all-gathered over NCCL) folded by zk_points_fold equal the full MSM."""
+    import torch
+    n = 6000
+    bases = co.g1_fixed_base(sy.random_fr_limbs(n, 31))
+    scal = sy.random_fr_limbs(n, 32)
+    half = n // 2
+    shards = [(0, half), (half, n)]
+    psz = zk.partial_size(1)
+    d_all = torch.zeros(psz * 2, dtype=torch.uint8, device="cuda")
+    keep = []
+    for k, (lo, hi) in enumerate(shards):
+        b = zk.Bases(ctx, 1, bases[lo:hi], window_bits=10)
+        d = torch.from_numpy(np.ascontiguousarray(scal[lo:hi]).view(np.int64)).cuda()
+        torch.cuda.synchronize()
+        zk.multiexp_partial_device(b, d.data_ptr(), hi - lo, d_all.data_ptr() + k * psz)
+        keep.append((b, d))
+    got = zk.points_fold(ctx, 1, d_all.data_ptr(), 2)
+    assert got == _enc(1, co.g1_msm(bases, scal))
+    for b, _ in keep:
+        b.free()
+
+
+def test_msm_g2_batch_and_adhoc(ctx):
+    import torch
+    n, batch = 1500, 3
+    bases = co.g2_fixed_base(sy.random_fr_limbs(n, 41))
+    scal = sy.random_fr_limbs(n * batch, 42).reshape(batch, n, 4)
+    scal[1, :, :] = 0; scal[1, ::3, 0] = 1                      # a witness-like vector: zeros and ones only
+    b = zk.Bases(ctx, 2, bases, window_bits=8)
+    d = torch.from_numpy(scal.view(np.int64)).cuda()
+    torch.cuda.synchronize()
+    got = zk.multiexp_device(b, d.data_ptr(), n, batch)
+    for k in range(batch):
+        assert got[192 * k:192 * k + 192] == _enc(2, co.g2_msm(bases, scal[k]))
+    b.free()
+    b = zk.Bases(ctx, 2, bases, window_bits=7, precompute=False)    # ad-hoc path: one bucket set per window + Horner
+    assert zk.multiexp(b, scal[0]) == _enc(2, co.g2_msm(bases, scal[0]))
+    b.free()

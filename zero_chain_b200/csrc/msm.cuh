@@ -129,16 +129,27 @@ static __global__ void __launch_bounds__(SORT_THREADS) k_scatter(const uint32_t 
 
 // ---- generic exclusive scan of u32 (three-phase; out[n] = total) -----------------------------------
 constexpr int SCAN_T = 256, SCAN_E = 8, SCAN_B = SCAN_T * SCAN_E;
+// number of tasks of a bucket with v entries for task length L: round to nearest (at least one), so that the
+// task count tracks total/L instead of overshooting by half a task per bucket (k_accumulate splits evenly)
 template <bool TASKS>
 __device__ __forceinline__ uint32_t scan_load(const uint32_t *in, size_t i, uint32_t task_len) {
     uint32_t v = in[i];
-    return TASKS ? (v + task_len - 1) / task_len : v;
+    if (!TASKS) return v;
+    if (v == 0) return 0;
+    uint32_t t = (v + task_len / 2) / task_len;
+    return t ? t : 1;
 }
-// task length from the number of non-zero entries (bucket_off[NB]): keeps ~TARGET_TASKS tasks in flight
-static __global__ void k_pick_task_len(const uint32_t *__restrict__ total_entries, uint32_t *__restrict__ task_len) {
-    uint32_t t = (*total_entries + TARGET_TASKS - 1) / TARGET_TASKS;
+// Task length from the number of non-zero entries (bucket_off[NB]).  Tasks all take the same time, so the
+// accumulation kernel runs in waves of `capacity` (= resident threads) tasks; the length is chosen so that the
+// task count is just under a whole number of waves (a trailing partial wave costs a full wave's latency).
+static __global__ void k_pick_task_len(const uint32_t *__restrict__ total_entries, uint32_t *__restrict__ task_len, uint32_t capacity) {
+    uint32_t total = *total_entries;
+    uint32_t waves = (total + (uint32_t)TASK_LEN_MAX * capacity - 1) / ((uint32_t)TASK_LEN_MAX * capacity);
+    if (waves < 2) waves = 2;                                   // small inputs: at least two waves of short tasks
+    uint32_t target = (uint32_t)(0.97f * (float)waves * (float)capacity);
+    uint32_t t = (total + target - 1) / (target ? target : 1);
     if (t < (uint32_t)TASK_LEN_MIN) t = TASK_LEN_MIN;
-    if (t > (uint32_t)TASK_LEN_MAX) t = TASK_LEN_MAX;
+    if (t > (uint32_t)TASK_LEN_MAX + 8) t = TASK_LEN_MAX + 8;
     *task_len = t;
 }
 // TASKS: scan ceil(in / *task_len_p) instead of in

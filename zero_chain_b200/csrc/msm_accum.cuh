@@ -8,7 +8,7 @@
 
 namespace zkmsm {
 
-constexpr int TASK_LEN_MAX = 64;          // max mixed additions per accumulate task
+constexpr int TASK_LEN_MAX = 64;          // target upper bound of mixed additions per accumulate task
 constexpr int TASK_LEN_MIN = 4;
 constexpr uint32_t TARGET_TASKS = 148u * 1024u;   // aim for >= ~1k resident tasks per SM so small / skewed MSMs still fill the GPU
 
@@ -25,8 +25,7 @@ __device__ __forceinline__ Affine<F> load_affine(const Affine<F> *__restrict__ p
 template <class F, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_accumulate(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ sorted,
                                                     const uint32_t *__restrict__ bucket_off, const uint32_t *__restrict__ task_off,
-                                                    uint32_t n_buckets, const uint32_t *__restrict__ task_len_p, XYZZ<F> *__restrict__ partials) {
-    (void)task_len_p;
+                                                    uint32_t n_buckets, XYZZ<F> *__restrict__ partials) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t n_tasks = task_off[n_buckets];
     if (t >= n_tasks) return;

@@ -30,8 +30,8 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
     if (E >= ((size_t)1 << 31)) { zk_set_error("MSM too large for 31-bit entry payloads (n*W*batch = %zu)", E); return ZK_ERR_INVALID; }
     const int tiles = (int)((e_dom + TILE - 1) / TILE);
     const size_t NB = n_dom * nbins;
-    // tasks: ceil(size_b / task_len) summed over buckets <= total/task_len + NB, task_len = clamp(ceil(total/TARGET), MIN, MAX)
-    size_t t_max = E / TASK_LEN_MAX; if (t_max < 2 * (size_t)TARGET_TASKS) t_max = 2 * (size_t)TARGET_TASKS; if (t_max > E / TASK_LEN_MIN + 1) t_max = E / TASK_LEN_MIN + 1;
+    // tasks: round(size_b / task_len) >= 1 per non-empty bucket, summed <= total/task_len + NB (k_pick_task_len)
+    size_t t_max = E / TASK_LEN_MAX + 2 * (size_t)TARGET_TASKS + 1;
     t_max += NB + 1;
     const size_t pt = sizeof(XYZZ<F>);
     ZK_TRY(ctx->digits.reserve(E * 4));
@@ -100,7 +100,8 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
         }
     }
     uint32_t *d_task_len = (uint32_t *)(ctx->d_err + 8);
-    k_pick_task_len<<<1, 1, 0, st>>>(cur_off + NB, d_task_len);
+    const uint32_t capacity = (uint32_t)ctx->sm_count * 3u * 128u;      // k_accumulate: 3 CTAs of 128 threads per SM
+    k_pick_task_len<<<1, 1, 0, st>>>(cur_off + NB, d_task_len, capacity);
     exclusive_scan<true>(cur_sizes, ctx->task_off.as<uint32_t>(), NB, ctx->scan_scratch.as<uint32_t>(), st, d_task_len);
     // 3. accumulate + combine.  The payload of an entry is its position in the domain = [w][i] index;
     //    with tables that is the table index when n == b->n (checked by the callers).
@@ -113,9 +114,9 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
         const Affine<F> *tb = cur_pts;
         const uint32_t *so = cur_sorted, *bo = cur_off, *to = ctx->task_off.as<uint32_t>();
         unsigned grid = (unsigned)((t_max + 127) / 128);
-        if (minb == 3) k_accumulate<F, 3><<<grid, 128, 0, st>>>(tb, so, bo, to, (uint32_t)NB, d_task_len, partials);
-        else if (minb == 4) k_accumulate<F, 4><<<grid, 128, 0, st>>>(tb, so, bo, to, (uint32_t)NB, d_task_len, partials);
-        else k_accumulate<F, 2><<<grid, 128, 0, st>>>(tb, so, bo, to, (uint32_t)NB, d_task_len, partials);
+        if (minb == 3) k_accumulate<F, 3><<<grid, 128, 0, st>>>(tb, so, bo, to, (uint32_t)NB, partials);
+        else if (minb == 4) k_accumulate<F, 4><<<grid, 128, 0, st>>>(tb, so, bo, to, (uint32_t)NB, partials);
+        else k_accumulate<F, 2><<<grid, 128, 0, st>>>(tb, so, bo, to, (uint32_t)NB, partials);
     }
     if (ctx->prof_on) { cudaEventRecord(ev1, st); ctx->prof_events.push_back(ev0); ctx->prof_events.push_back(ev1); }
     const size_t sm_warp = 4 * 32 * pt;      // 4 warps x 32 points
