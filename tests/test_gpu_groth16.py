@@ -141,3 +141,23 @@ def test_gpu_proof_verifies_by_pairing(ctx):
     except ValueError:
         pass                                                              # not even a curve point any more
     params.free()
+
+
+def test_prove_anonymous_transfer_shape(ctx):
+    """the reference's other KeyContext flavour — the anonymous_transfer circuit shape
+    (domain 2^16, |h| 65 535, |l| 50 429, |a| 39 133, |b| 31 257, 105 public inputs) — through the same kernels."""
+    r1cs = sy.make_r1cs(seed=11, **sy.ANON_SHAPE)
+    crs = sy.make_toy_crs(r1cs, co.g1_fixed_base, co.g2_fixed_base, seed=12)
+    params = zk.Parameters.read(ctx, crs.params_bytes, checked=False)
+    assert (params.n_h, params.n_l, params.n_a, params.n_b_g1, params.n_ic) == (65535, 50429, 39133, 31257, 105)
+    oparams = co.Params(crs.params_bytes, checked=False)
+    z0, p0 = _witness(r1cs, 21)
+    z1, p1 = _witness(r1cs, 22)
+    rs, ss = [0x1111, 0x2222], [0x3333, 0x4444]
+    got = zk.create_proof_batch([p0, p1], params, rs, ss)
+    for k, pa in enumerate((p0, p1)):
+        want = oparams.prove(pa.a, pa.b, pa.c, pa.input_assignment, pa.aux_assignment, pa.a_aux_density, pa.b_input_density, pa.b_aux_density, rs[k], ss[k])
+        assert got[192 * k:192 * k + 192] == want
+    A, B, C = sy.expected_proof_scalars(crs, z0, rs[0], ss[0])
+    assert got[:192] == pr.proof_bytes(pr.ec_mul(pr.FQ, pr.G1_GEN, A), pr.ec_mul(pr.FQ2, pr.G2_GEN, B), pr.ec_mul(pr.FQ, pr.G1_GEN, C))
+    params.free()

@@ -27,6 +27,10 @@ R = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
 _ROOT = pow(7, (R - 1) >> 32, R)
 
 CONF_SHAPE = dict(n_constraints=19974, n_inputs=23, n_aux=19955, a_aux_density=15575, b_density=12402)
+# The reference's second circuit: anonymous_transfer, ~50 634 constraints, 105 inputs, domain 2^16;
+# CRS vector lengths parsed from zface/params/anony_pk.dat: h 65 535, l 50 429, a 39 133, b 31 257, ic 105
+# (core/proofs/src/circuit/anonymous_transfer.rs:449-451, core/proofs/src/anonymous.rs:165).
+ANON_SHAPE = dict(n_constraints=50634, n_inputs=105, n_aux=50429, a_aux_density=39028, b_density=31257)
 
 
 class SplitMix64:
