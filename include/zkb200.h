@@ -125,6 +125,23 @@ int zk_groth16_prove_batch(zk_ctx *ctx, const zk_params *p, size_t batch,
                            const uint8_t *a_aux_density, const uint8_t *b_input_density, const uint8_t *b_aux_density,
                            const uint64_t *r, const uint64_t *s, uint8_t *proofs_out);
 
+/* ---- proving straight from the witness (synthesis off the critical path) --------------
+ * For a FIXED circuit the constraint matrices A, B, C are known after one synthesis pass (bellman's
+ * KeypairAssembly records them as at/bt/ct during parameter generation).  Loaded once in CSR form, the device
+ * evaluates <A_j,z>, <B_j,z>, <C_j,z> itself, so per proof only the assignment z = (inputs | aux) crosses PCIe
+ * (0.64 MB instead of 2.6 MB for confidential_transfer) and ProvingAssignment::enforce's host arithmetic disappears.
+ *   row_ptr[n_constraints + 1], col[nnz] (variable index: < n_inputs = input, else n_inputs + aux index),
+ *   coeff[nnz][4] canonical Fr.  The `input_i * 0 = 0` rows are appended by the library; densities are derived. */
+typedef struct zk_r1cs zk_r1cs;
+int zk_r1cs_load(zk_ctx *ctx, size_t n_constraints, size_t n_inputs, size_t n_aux,
+                 const uint32_t *a_row_ptr, const uint32_t *a_col, const uint64_t *a_coeff,
+                 const uint32_t *b_row_ptr, const uint32_t *b_col, const uint64_t *b_coeff,
+                 const uint32_t *c_row_ptr, const uint32_t *c_col, const uint64_t *c_coeff, zk_r1cs **out);
+void zk_r1cs_free(zk_r1cs *r1cs);
+int zk_groth16_prove_witness_batch(zk_ctx *ctx, const zk_params *p, const zk_r1cs *r1cs, size_t batch,
+                                   const uint64_t *input_assignment, const uint64_t *aux_assignment,
+                                   const uint64_t *r, const uint64_t *s, uint8_t *proofs_out);
+
 /* ---- utilities / diagnostics ------------------------------------------------------------------ */
 /* out[i] = scalars[i] * base (limb form in, limb form out); group 1 or 2.  Used to build synthetic
  * CRS / test vectors on the device (fixed-base scalar multiplication). */

@@ -161,3 +161,27 @@ def test_prove_anonymous_transfer_shape(ctx):
     A, B, C = sy.expected_proof_scalars(crs, z0, rs[0], ss[0])
     assert got[:192] == pr.proof_bytes(pr.ec_mul(pr.FQ, pr.G1_GEN, A), pr.ec_mul(pr.FQ2, pr.G2_GEN, B), pr.ec_mul(pr.FQ, pr.G1_GEN, C))
     params.free()
+
+
+@pytest.mark.parametrize("shape", ["tiny", "mid"])
+def test_prove_from_witness_matches_evals_path(ctx, shape):
+    """with the fixed constraint system resident on the device, the per-constraint evaluations
+    <A_j,z>, <B_j,z>, <C_j,z> (ProvingAssignment::enforce on the host in bellman) are computed by the GPU from the
+    assignment alone; proofs must equal the host-evaluated path and the oracle byte for byte."""
+    r1cs = sy.make_r1cs(seed=3, **SHAPES[shape])
+    crs = sy.make_toy_crs(r1cs, co.g1_fixed_base, co.g2_fixed_base, seed=4)
+    params = zk.Parameters.read(ctx, crs.params_bytes, checked=False)
+    oparams = co.Params(crs.params_bytes, checked=False)
+    cs = zk.ConstraintSystem(ctx, r1cs.n_inputs, r1cs.n_aux, r1cs.A, r1cs.B, r1cs.C)
+    batch = 3
+    ws = [_witness(r1cs, 40 + k) for k in range(batch)]
+    rs = [0xAA + k for k in range(batch)]; ss = [0xBB00 + k for k in range(batch)]
+    inputs = np.stack([w[1].input_assignment for w in ws]); aux = np.stack([w[1].aux_assignment for w in ws])
+    got = zk.create_proof_from_witness_batch(cs, params, batch, inputs, aux, co.ints_to_limbs(rs, 4), co.ints_to_limbs(ss, 4))
+    assert got == zk.create_proof_batch([w[1] for w in ws], params, rs, ss)
+    pa = ws[1][1]
+    assert got[192:384] == oparams.prove(pa.a, pa.b, pa.c, pa.input_assignment, pa.aux_assignment, pa.a_aux_density, pa.b_input_density, pa.b_aux_density, rs[1], ss[1])
+    bad = aux.copy(); bad[0, 0, :] = 0xFFFFFFFFFFFFFFFF
+    with pytest.raises(zk.SynthesisError):
+        zk.create_proof_from_witness_batch(cs, params, batch, inputs, bad, co.ints_to_limbs(rs, 4), co.ints_to_limbs(ss, 4))   # non-canonical
+    cs.free(); params.free()

@@ -23,6 +23,15 @@ struct zk_params {
     zk_bases *h = nullptr, *l = nullptr, *a = nullptr, *b1 = nullptr, *b2 = nullptr;   // extended vectors (see above)
 };
 
+// The fixed constraint system of one circuit, resident on the device in CSR form.
+struct zk_r1cs {
+    int device = 0;
+    size_t n_c = 0, n_in = 0, n_aux = 0;
+    uint32_t *d_row_ptr[3] = {nullptr, nullptr, nullptr}, *d_col[3] = {nullptr, nullptr, nullptr};
+    void *d_coeff[3] = {nullptr, nullptr, nullptr};
+    std::vector<uint8_t> a_aux_density, b_input_density, b_aux_density;     // DensityTracker bits, derived from A and B
+};
+
 static uint32_t rd_u32be(const uint8_t *p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
 
 extern "C" void zk_params_free(zk_params *p) {
@@ -146,8 +155,13 @@ static int prove_impl(zk_ctx *ctx, const zk_params *p, size_t batch,
                       const uint64_t *a_ev, const uint64_t *b_ev, const uint64_t *c_ev, size_t n_c,
                       const uint64_t *inputs, size_t n_in, const uint64_t *aux, size_t n_aux,
                       const uint8_t *a_aux_d, const uint8_t *b_in_d, const uint8_t *b_aux_d,
-                      const uint64_t *r, const uint64_t *s, uint8_t *proofs_out) {
-    if (!ctx || !p || !a_ev || !b_ev || !c_ev || !inputs || !aux || !a_aux_d || !b_in_d || !b_aux_d || !r || !s || !proofs_out) {
+                      const uint64_t *r, const uint64_t *s, uint8_t *proofs_out, const zk_r1cs *r1cs = nullptr) {
+    if (r1cs) {     // evaluations are computed on the device from the witness; densities come with the constraint system
+        if (r1cs->n_in != n_in || r1cs->n_aux != n_aux) { zk_set_error("witness sizes do not match the constraint system"); return ZK_ERR_ASSIGNMENT_MISSING; }
+        a_aux_d = r1cs->a_aux_density.data(); b_in_d = r1cs->b_input_density.data(); b_aux_d = r1cs->b_aux_density.data();
+        n_c = r1cs->n_c + r1cs->n_in;
+    }
+    if (!ctx || !p || (!r1cs && (!a_ev || !b_ev || !c_ev)) || !inputs || !aux || !a_aux_d || !b_in_d || !b_aux_d || !r || !s || !proofs_out) {
         zk_set_error("zk_groth16_prove: NULL argument"); return ZK_ERR_INVALID;
     }
     if (batch == 0 || batch > 4096 || n_c == 0) { zk_set_error("zk_groth16_prove: bad batch / constraint count"); return ZK_ERR_INVALID; }
@@ -196,10 +210,20 @@ static int prove_impl(zk_ctx *ctx, const zk_params *p, size_t batch,
     ZK_CUDA(cudaMemcpyAsync(d_s, s, batch * 32, cudaMemcpyHostToDevice, st));
     ZK_TRY(zk_fr_blinding_terms(ctx, d_r, d_s, batch, d_terms));
     // ---- h: 3 x (ifft, coset_fft), quotient, icoset_fft ----
-    const uint64_t *evs[3] = {a_ev, b_ev, c_ev};
-    for (int w = 0; w < 3; w++) {
-        ZK_CUDA(cudaMemcpyAsync(ctx->g_b.p, evs[w], batch * n_c * 32, cudaMemcpyHostToDevice, st));
-        ZK_TRY(zk_fr_load_evals(ctx, ctx->g_b.p, n_c, log_m, w, batch, ctx->g_a.p));
+    uint4 *d_in = ctx->g_c.as<uint4>(), *d_aux = d_in + batch * n_in * 2;
+    ZK_CUDA(cudaMemcpyAsync(d_in, inputs, batch * n_in * 32, cudaMemcpyHostToDevice, st));
+    ZK_CUDA(cudaMemcpyAsync(d_aux, aux, batch * n_aux * 32, cudaMemcpyHostToDevice, st));
+    if (r1cs) {
+        ZK_TRY(ctx->g_b.reserve(batch * (n_in + n_aux) * 32));       // z in Montgomery form
+        ZK_TRY(zk_fr_witness_to_mont(ctx, d_in, n_in, d_aux, n_aux, batch, ctx->g_b.p));
+        for (int w = 0; w < 3; w++)
+            ZK_TRY(zk_fr_r1cs_eval(ctx, r1cs->d_row_ptr[w], r1cs->d_col[w], r1cs->d_coeff[w], ctx->g_b.p, r1cs->n_c, n_in, n_in + n_aux, log_m, w, batch, ctx->g_a.p));
+    } else {
+        const uint64_t *evs[3] = {a_ev, b_ev, c_ev};
+        for (int w = 0; w < 3; w++) {
+            ZK_CUDA(cudaMemcpyAsync(ctx->g_b.p, evs[w], batch * n_c * 32, cudaMemcpyHostToDevice, st));
+            ZK_TRY(zk_fr_load_evals(ctx, ctx->g_b.p, n_c, log_m, w, batch, ctx->g_a.p));
+        }
     }
     ZK_TRY(zk_ntt_run(ctx, ctx->g_a.p, log_m, ZK_NTT_IFFT, 3 * batch));
     ZK_TRY(zk_ntt_run(ctx, ctx->g_a.p, log_m, ZK_NTT_COSET_FFT, 3 * batch));
@@ -211,10 +235,7 @@ static int prove_impl(zk_ctx *ctx, const zk_params *p, size_t batch,
     k_put_terms<<<(unsigned)((batch + 63) / 64), 64, 0, st>>>((const uint4 *)d_terms, 3, 3, 1, scal, nH, m - 1, batch);
     ZK_TRY(zk_msm_run(ctx, p->h, scal, nH, batch));
     ZK_CUDA(cudaMemcpyAsync(d_H, ctx->result.p, batch * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, st));
-    // ---- assignments ----
-    uint4 *d_in = ctx->g_c.as<uint4>(), *d_aux = d_in + batch * n_in * 2;
-    ZK_CUDA(cudaMemcpyAsync(d_in, inputs, batch * n_in * 32, cudaMemcpyHostToDevice, st));
-    ZK_CUDA(cudaMemcpyAsync(d_aux, aux, batch * n_aux * 32, cudaMemcpyHostToDevice, st));
+    // ---- assignments (already on the device: d_in, d_aux) ----
     // L
     ZK_TRY(zk_msm_run(ctx, p->l, d_aux, n_aux, batch));
     ZK_CUDA(cudaMemcpyAsync(d_L, ctx->result.p, batch * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, st));
@@ -253,4 +274,57 @@ extern "C" int zk_groth16_prove(zk_ctx *ctx, const zk_params *p,
                                 const uint8_t *d1, const uint8_t *d2, const uint8_t *d3,
                                 const uint64_t r[4], const uint64_t s[4], uint8_t out[192]) {
     return prove_impl(ctx, p, 1, a, b, c, n_c, inputs, n_in, aux, n_aux, d1, d2, d3, r, s, out);
+}
+
+// ---- fixed constraint system on the device ---------------------------------------------------------
+extern "C" void zk_r1cs_free(zk_r1cs *q) {
+    if (!q) return;
+    cudaSetDevice(q->device);
+    for (int w = 0; w < 3; w++) { if (q->d_row_ptr[w]) cudaFree(q->d_row_ptr[w]); if (q->d_col[w]) cudaFree(q->d_col[w]); if (q->d_coeff[w]) cudaFree(q->d_coeff[w]); }
+    delete q;
+}
+extern "C" int zk_r1cs_load(zk_ctx *ctx, size_t n_constraints, size_t n_inputs, size_t n_aux,
+                            const uint32_t *a_row_ptr, const uint32_t *a_col, const uint64_t *a_coeff,
+                            const uint32_t *b_row_ptr, const uint32_t *b_col, const uint64_t *b_coeff,
+                            const uint32_t *c_row_ptr, const uint32_t *c_col, const uint64_t *c_coeff, zk_r1cs **out) {
+    if (!ctx || !out || !a_row_ptr || !b_row_ptr || !c_row_ptr) { zk_set_error("zk_r1cs_load: NULL argument"); return ZK_ERR_INVALID; }
+    if (n_constraints == 0 || n_inputs == 0) { zk_set_error("zk_r1cs_load: empty constraint system"); return ZK_ERR_INVALID; }
+    ZK_TRY(zk_use_device(ctx));
+    const uint32_t *rp[3] = {a_row_ptr, b_row_ptr, c_row_ptr}, *cl[3] = {a_col, b_col, c_col};
+    const uint64_t *cf[3] = {a_coeff, b_coeff, c_coeff};
+    const size_t nv = n_inputs + n_aux;
+    zk_r1cs *q = new zk_r1cs();
+    q->device = ctx->device; q->n_c = n_constraints; q->n_in = n_inputs; q->n_aux = n_aux;
+    q->a_aux_density.assign(n_aux ? n_aux : 1, 0); q->b_input_density.assign(n_inputs, 0); q->b_aux_density.assign(n_aux ? n_aux : 1, 0);
+    for (int w = 0; w < 3; w++) {
+        size_t nnz = rp[w][n_constraints];
+        if (rp[w][0] != 0 || (nnz && (!cl[w] || !cf[w]))) { zk_r1cs_free(q); zk_set_error("zk_r1cs_load: malformed CSR"); return ZK_ERR_INVALID; }
+        for (size_t j = 0; j < n_constraints; j++) if (rp[w][j] > rp[w][j + 1]) { zk_r1cs_free(q); zk_set_error("zk_r1cs_load: row_ptr not monotone"); return ZK_ERR_INVALID; }
+        for (size_t k = 0; k < nnz; k++) {
+            uint32_t v = cl[w][k];
+            if (v >= nv) { zk_r1cs_free(q); zk_set_error("zk_r1cs_load: variable index %u out of range", v); return ZK_ERR_INVALID; }
+            if (w == 0 && v >= n_inputs) q->a_aux_density[v - n_inputs] = 1;
+            if (w == 1) { if (v >= n_inputs) q->b_aux_density[v - n_inputs] = 1; else q->b_input_density[v] = 1; }
+        }
+        cudaError_t e1 = cudaMalloc(&q->d_row_ptr[w], (n_constraints + 1) * 4), e2 = cudaMalloc(&q->d_col[w], (nnz + 1) * 4), e3 = cudaMalloc(&q->d_coeff[w], (nnz + 1) * 32);
+        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { zk_r1cs_free(q); zk_set_error("zk_r1cs_load: cudaMalloc failed"); return ZK_ERR_CUDA; }
+        ZK_CUDA(cudaMemcpyAsync(q->d_row_ptr[w], rp[w], (n_constraints + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (nnz) {
+            ZK_CUDA(cudaMemcpyAsync(q->d_col[w], cl[w], nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+            ZK_TRY(ctx->stage_a.reserve(nnz * 32));
+            ZK_CUDA(cudaMemcpyAsync(ctx->stage_a.p, cf[w], nnz * 32, cudaMemcpyHostToDevice, ctx->stream));
+            ZK_TRY(zk_fr_to_mont(ctx, ctx->stage_a.p, nnz, q->d_coeff[w]));
+            ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    int r = zk_check_err_flag(ctx);
+    if (r) { zk_r1cs_free(q); return r; }
+    *out = q;
+    return ZK_OK;
+}
+extern "C" int zk_groth16_prove_witness_batch(zk_ctx *ctx, const zk_params *p, const zk_r1cs *q, size_t batch,
+                                              const uint64_t *inputs, const uint64_t *aux, const uint64_t *r, const uint64_t *s, uint8_t *proofs_out) {
+    if (!q) { zk_set_error("zk_groth16_prove_witness_batch: NULL constraint system"); return ZK_ERR_INVALID; }
+    if (q->device != ctx->device) { zk_set_error("constraint system lives on device %d, context on %d", q->device, ctx->device); return ZK_ERR_INVALID; }
+    return prove_impl(ctx, p, batch, nullptr, nullptr, nullptr, 0, inputs, q->n_in, aux, q->n_aux, nullptr, nullptr, nullptr, r, s, proofs_out, q);
 }

@@ -86,3 +86,7 @@ int zk_fr_quotient(zk_ctx *ctx, const void *d_abc, unsigned log_m, size_t batch,
 int zk_fr_into_repr(zk_ctx *ctx, const void *d_h, unsigned log_m, size_t n_out, size_t n_total, size_t batch, void *d_scal);
 int zk_fr_blinding_terms(zk_ctx *ctx, const void *d_r, const void *d_s, size_t batch, void *d_out);
 int zk_check_err_flag(zk_ctx *ctx);
+int zk_fr_to_mont(zk_ctx *ctx, const void *d_in, size_t n, void *d_out);
+int zk_fr_witness_to_mont(zk_ctx *ctx, const void *d_inputs, size_t n_in, const void *d_aux, size_t n_aux, size_t batch, void *d_z);
+int zk_fr_r1cs_eval(zk_ctx *ctx, const uint32_t *d_row_ptr, const uint32_t *d_col, const void *d_coeff, const void *d_z, size_t n_c, size_t n_in,
+                    size_t nv, unsigned log_m, int which, size_t batch, void *d_dst);

@@ -303,7 +303,58 @@ __global__ void k_blinding_terms(const Fr *__restrict__ r, const Fr *__restrict_
     Fr rs = (Fr::from_canonical(rc) * Fr::from_canonical(sc)).neg().to_canonical();
     store_fr(out + b * 4, one); store_fr(out + b * 4 + 1, rc); store_fr(out + b * 4 + 2, sc); store_fr(out + b * 4 + 3, rs);
 }
+// z[b][v] = from_repr(inputs | aux) for the R1CS evaluation
+__global__ void k_witness_to_mont(const Fr *__restrict__ inputs, size_t n_in, const Fr *__restrict__ aux, size_t n_aux, Fr *__restrict__ z, int *err) {
+    size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y, nv = n_in + n_aux;
+    if (v >= nv) return;
+    Fr c = v < n_in ? load_fr(inputs + b * n_in + v) : load_fr(aux + b * n_aux + (v - n_in));
+    if (!Fr::canonical_lt_mod(c)) atomicExch(err, 1);
+    store_fr(z + b * nv + v, Fr::from_canonical(c));
+}
+// dst[b][which][i] = <M_i, z_b> for i < n_c (CSR row i of the matrix `which`), the appended `input_i * 0 = 0` rows for
+// n_c <= i < n_c + n_in (A only: the input's value), zero padding up to m.  What ProvingAssignment::enforce computes on
+// the host in bellman, moved to the device for a fixed constraint system.
+__global__ void k_r1cs_eval(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ col, const Fr *__restrict__ coeff,
+                            const Fr *__restrict__ z, size_t n_c, size_t n_in, size_t nv, unsigned log_m, int which, Fr *__restrict__ dst) {
+    size_t m = (size_t)1 << log_m;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (i >= m) return;
+    const Fr *zb = z + b * nv;
+    Fr acc = Fr::zero();
+    if (i < n_c) {
+        for (uint32_t k = row_ptr[i]; k < row_ptr[i + 1]; k++) acc = acc + load_fr(coeff + k) * load_fr(zb + col[k]);
+    } else if (which == 0 && i < n_c + n_in) acc = load_fr(zb + (i - n_c));
+    store_fr(dst + ((b * 3 + which) << log_m) + i, acc);
+}
+// coefficients canonical -> Montgomery (once, at zk_r1cs_load)
+__global__ void k_fr_to_mont(const Fr *__restrict__ in, size_t n, Fr *__restrict__ out, int *err) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr c = load_fr(in + i);
+    if (!Fr::canonical_lt_mod(c)) atomicExch(err, 1);
+    store_fr(out + i, Fr::from_canonical(c));
+}
 }  // namespace
+
+int zk_fr_to_mont(zk_ctx *ctx, const void *d_in, size_t n, void *d_out) {
+    if (n) k_fr_to_mont<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const Fr *)d_in, n, (Fr *)d_out, ctx->d_err);
+    ZK_CUDA(cudaGetLastError());
+    return ZK_OK;
+}
+int zk_fr_witness_to_mont(zk_ctx *ctx, const void *d_inputs, size_t n_in, const void *d_aux, size_t n_aux, size_t batch, void *d_z) {
+    size_t nv = n_in + n_aux;
+    k_witness_to_mont<<<dim3((unsigned)((nv + 255) / 256), (unsigned)batch), 256, 0, ctx->stream>>>((const Fr *)d_inputs, n_in, (const Fr *)d_aux, n_aux, (Fr *)d_z, ctx->d_err);
+    ZK_CUDA(cudaGetLastError());
+    return ZK_OK;
+}
+int zk_fr_r1cs_eval(zk_ctx *ctx, const uint32_t *d_row_ptr, const uint32_t *d_col, const void *d_coeff, const void *d_z, size_t n_c, size_t n_in,
+                    size_t nv, unsigned log_m, int which, size_t batch, void *d_dst) {
+    size_t m = (size_t)1 << log_m;
+    k_r1cs_eval<<<dim3((unsigned)((m + 127) / 128), (unsigned)batch), 128, 0, ctx->stream>>>(d_row_ptr, d_col, (const Fr *)d_coeff, (const Fr *)d_z, n_c, n_in, nv,
+                                                                                          log_m, which, (Fr *)d_dst);
+    ZK_CUDA(cudaGetLastError());
+    return ZK_OK;
+}
 
 int zk_fr_load_evals(zk_ctx *ctx, const void *d_src, size_t n_c, unsigned log_m, int which, size_t batch, void *d_dst) {
     size_t m = (size_t)1 << log_m;

@@ -247,6 +247,52 @@ def create_proof_batch(provers, params: Parameters, rs, ss) -> bytes:
     return out.tobytes()
 
 
+class ConstraintSystem:
+    """The fixed R1CS of a circuit resident on the device (CSR), so proofs can be made straight from assignments
+    (zk_groth16_prove_witness_batch).  rows_*: per constraint a list of (variable, coefficient) with variable < n_inputs
+    for inputs and n_inputs + i for aux i — the at/bt/ct that bellman's KeypairAssembly collects."""
+
+    def __init__(self, ctx: Context, n_inputs: int, n_aux: int, rows_a, rows_b, rows_c):
+        self.ctx, self.n_inputs, self.n_aux = ctx, n_inputs, n_aux
+        n_c = len(rows_a)
+        assert len(rows_b) == n_c and len(rows_c) == n_c
+        arrs = []
+        for rows in (rows_a, rows_b, rows_c):
+            rp = np.zeros(n_c + 1, np.uint32)
+            rp[1:] = np.cumsum([len(r) for r in rows])
+            col = np.array([v for r in rows for v, _ in r] or [0], np.uint32)
+            cf = np.zeros((max(1, int(rp[-1])), 4), np.uint64)
+            k = 0
+            for r in rows:
+                for _, c in r:
+                    for j in range(4):
+                        cf[k, j] = (c >> (64 * j)) & 0xFFFFFFFFFFFFFFFF
+                    k += 1
+            arrs += [rp, col, cf]
+        self._h = C.c_void_p()
+        _ck(_lib.lib().zk_r1cs_load(ctx._h, n_c, n_inputs, n_aux, *[_p(a) for a in arrs], C.byref(self._h)))
+
+    def free(self):
+        if self._h:
+            _lib.lib().zk_r1cs_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def create_proof_from_witness_batch(cs: ConstraintSystem, params: Parameters, batch: int, inputs, aux, r, s) -> bytes:
+    """inputs [batch][n_inputs][4], aux [batch][n_aux][4] canonical; r, s [batch][4] -> batch * 192 bytes."""
+    inputs, aux = _u64(inputs, (batch, cs.n_inputs, 4)), _u64(aux, (batch, cs.n_aux, 4))
+    r, s = _u64(r, (batch, 4)), _u64(s, (batch, 4))
+    out = np.zeros(192 * batch, np.uint8)
+    _ck(_lib.lib().zk_groth16_prove_witness_batch(params.ctx._h, params._h, cs._h, batch, _p(inputs), _p(aux), _p(r), _p(s), _p(out)))
+    return out.tobytes()
+
+
 def create_proof_batch_raw(params: Parameters, batch: int, a, b, c, inputs, aux, a_aux_density, b_input_density, b_aux_density, r, s) -> bytes:
     """Same as create_proof_batch with the per-proof arrays already concatenated ([batch][n][4] uint64, e.g. views
     of pinned host memory): exactly one zk_groth16_prove_batch call, no host-side copies."""
