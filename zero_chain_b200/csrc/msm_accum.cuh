@@ -41,13 +41,32 @@ __global__ void __launch_bounds__(128, MINB) k_accumulate(const Affine<F> *__res
     if (e1 > b0 + size) e1 = b0 + size;
     if (e0 >= e1) { partials[t] = XYZZ<F>::inf(); return; }
     XYZZ<F> acc = XYZZ<F>::inf();
+    // The next point is prefetched with cp.async into a per-thread shared-memory slot while the current mixed
+    // addition runs: the gather latency is hidden without holding a second point (24+ registers) live.
     // sorted == nullptr: the inputs are already-reduced affine points indexed by position (no sign)
+    constexpr int VEC = (int)(sizeof(Affine<F>) / 16);
+    __shared__ uint4 stage[128 * VEC];
+    uint4 *slot = stage + threadIdx.x * VEC;
+    const uint32_t slot_addr = (uint32_t)__cvta_generic_to_shared(slot);
+    auto prefetch = [&](uint32_t c) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(bases + (c & 0x7fffffffu));
+#pragma unroll
+        for (int k = 0; k < VEC; k++)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot_addr + 16u * k), "l"(src + k) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     uint32_t code = sorted ? sorted[e0] : e0;
-    Affine<F> nxt = load_affine(bases + (code & 0x7fffffffu));
+    prefetch(code);
     for (uint32_t e = e0; e < e1; e++) {
-        Affine<F> p = nxt;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        Affine<F> p;
+        {
+            uint4 *d = reinterpret_cast<uint4 *>(&p);
+#pragma unroll
+            for (int k = 0; k < VEC; k++) d[k] = slot[k];
+        }
         bool neg = code >> 31;
-        if (e + 1 < e1) { code = sorted ? sorted[e + 1] : e + 1; nxt = load_affine(bases + (code & 0x7fffffffu)); }
+        if (e + 1 < e1) { code = sorted ? sorted[e + 1] : e + 1; prefetch(code); }
         p.y = p.y.cneg(neg);
         acc.add_mixed(p);
     }
