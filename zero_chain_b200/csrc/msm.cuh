@@ -317,6 +317,56 @@ __global__ void __launch_bounds__(RED_T) k_finish_bits(const XYZZ<F> *__restrict
     }
     if (lane == 0) R[dom] = v;
 }
+// ---- two-level bucket reduction for many domains (batched proving) -----------------------------------------
+// sum_d d*B[d] with d = hi*S + lo (S = 2^s):  S * sum_hi hi*R_hi + sum_lo lo*C_lo,  R_hi / C_lo = row / column sums
+// of the bucket matrix.  Every bucket is added twice (instead of ~c/2 times by the per-bit subset sums); the two small
+// weighted sums that remain go through the per-bit kernels above.  Used when there are enough domains to fill the GPU
+// (work-bound regime); a single large MSM keeps the shallower per-bit scheme (latency-bound regime).
+// EIGHT lanes per (domain, row hi = 1..N/S) or (domain, column lo = 1..S-1): each lane adds every 8th element serially,
+// then a 3-level tree inside the group (a full warp per row would spend most of its issue slots in the tree).
+// rows[dom][hi-1], cols[dom][lo-1].
+template <class F>
+__global__ void __launch_bounds__(RED_T) k_rowcol_sums(const XYZZ<F> *__restrict__ B, int N, int s, int n_dom,
+                                                       XYZZ<F> *__restrict__ rows, XYZZ<F> *__restrict__ cols) {
+    extern __shared__ unsigned char smraw[];
+    const uint32_t lane = threadIdx.x & 31, sub = lane & 7;
+    XYZZ<F> *slot = reinterpret_cast<XYZZ<F> *>(smraw) + (threadIdx.x >> 5) * 32;
+    const int S = 1 << s, nr = N >> s, nc = S - 1;
+    const size_t n_items = (size_t)n_dom * (nr + nc);
+    size_t item = ((((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) << 2) + (lane >> 3);
+    const bool live = item < n_items;
+    int dom = 0, idx = 0;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    if (live) {
+        dom = (int)(item / (nr + nc)); idx = (int)(item % (nr + nc));
+        const XYZZ<F> *p = B + (size_t)dom * N;
+        if (idx < nr) {
+            int hi = idx + 1;
+            for (int lo = sub; lo < S; lo += 8) { int d = hi * S + lo; if (d <= N) acc.add(p[d - 1]); }
+        } else {
+            int lo = idx - nr + 1;
+            for (int hi = sub; hi <= nr; hi += 8) { int d = hi * S + lo; if (d <= N) acc.add(p[d - 1]); }
+        }
+    }
+    slot[lane] = acc;
+    __syncwarp();
+    for (int o = 4; o > 0; o >>= 1) {
+        if (sub < (uint32_t)o) { XYZZ<F> x = slot[lane]; x.add(slot[lane + o]); slot[lane] = x; }
+        __syncwarp();
+    }
+    if (live && sub == 0) { if (idx < nr) rows[(size_t)dom * nr + idx] = slot[lane]; else cols[(size_t)dom * nc + (idx - nr)] = slot[lane]; }
+}
+// thread per domain: R = 2^s * Rrows + Rcols
+template <class F>
+__global__ void k_join_rowcol(const XYZZ<F> *__restrict__ Rrows, const XYZZ<F> *__restrict__ Rcols, int s, int n_dom, XYZZ<F> *__restrict__ R) {
+    int dom = blockIdx.x * blockDim.x + threadIdx.x;
+    if (dom >= n_dom) return;
+    XYZZ<F> r = Rrows[dom];
+    for (int k = 0; k < s; k++) r = r.dbl();
+    r.add(Rcols[dom]);
+    R[dom] = r;
+}
+
 // single thread: out = sum_w 2^(c w) R[w]  (Horner over windows; ad-hoc MSM without tables)
 template <class F>
 __global__ void k_horner_windows(const XYZZ<F> *__restrict__ R, int W, int c, XYZZ<F> *__restrict__ out) {

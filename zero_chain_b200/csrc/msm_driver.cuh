@@ -130,14 +130,30 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
     k_combine_warp<F><<<(unsigned)((NB * 32 + 127) / 128), 128, sm_warp, st>>>(partials, ctx->task_off.as<uint32_t>(), (uint32_t)NB, buckets);
     // 4. bucket reduction per domain
     XYZZ<F> *part = ctx->red_part.as<XYZZ<F>>(), *X = ctx->red_x.as<XYZZ<F>>(), *R = ctx->result.as<XYZZ<F>>();
-    size_t n_w = (size_t)n_slices * n_bits * n_dom;
-    k_bit_sums<F><<<(unsigned)((n_w * 32 + RED_T - 1) / RED_T), RED_T, sm_warp, st>>>(buckets, nbins, n_slices, n_bits, (int)n_dom, part);
-    size_t n_g = n_dom * n_bits;
-    k_sum_points<F><<<(unsigned)((n_g * 32 + RED_T - 1) / RED_T), RED_T, sm_warp, st>>>(part, n_slices, (int)n_g, X);
-    if (tables) {
-        k_finish_bits<F><<<(unsigned)((n_dom * 32 + RED_T - 1) / RED_T), RED_T, sm_warp, st>>>(X, n_bits, (int)n_dom, R);
+    auto bit_reduce = [&](const XYZZ<F> *Bk, int N, int bits, XYZZ<F> *out) {     // out[dom] = sum_{d=1..N} d * Bk[dom][d-1]
+        int slices = (N / 2 + RED_SLICE / 2 - 1) / (RED_SLICE / 2); if (slices < 1) slices = 1;
+        size_t n_w = (size_t)slices * bits * n_dom, n_g = n_dom * (size_t)bits;
+        k_bit_sums<F><<<(unsigned)((n_w * 32 + RED_T - 1) / RED_T), RED_T, sm_warp, st>>>(Bk, N, slices, bits, (int)n_dom, part);
+        k_sum_points<F><<<(unsigned)((n_g * 32 + RED_T - 1) / RED_T), RED_T, sm_warp, st>>>(part, slices, (int)n_g, X);
+        k_finish_bits<F><<<(unsigned)((n_dom * 32 + RED_T - 1) / RED_T), RED_T, sm_warp, st>>>(X, bits, (int)n_dom, out);
+    };
+    if (tables && n_dom >= 8 && c >= 7) {
+        // many domains (batched proving): two-level row/column scheme, 2 additions per bucket (msm.cuh)
+        const int s = (c - 1) / 2, nr = nbins >> s, nc = (1 << s) - 1;
+        ZK_TRY(ctx->red_rows.reserve(n_dom * (size_t)(nr + nc + 2) * pt));
+        if (sm_warp > 48 * 1024) ZK_CUDA(cudaFuncSetAttribute(k_rowcol_sums<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_warp));
+        XYZZ<F> *rows = ctx->red_rows.as<XYZZ<F>>(), *cols = rows + n_dom * (size_t)nr, *Rr = R + n_dom + 1, *Rc = cols + n_dom * (size_t)nc;
+        ZK_TRY(ctx->result.reserve((2 * n_dom + batch + 2) * pt));
+        R = ctx->result.as<XYZZ<F>>(); Rr = R + n_dom + 1;
+        size_t n_w = n_dom * (size_t)(nr + nc);
+        k_rowcol_sums<F><<<(unsigned)((((n_w + 3) / 4) * 32 + RED_T - 1) / RED_T), RED_T, sm_warp, st>>>(buckets, nbins, s, (int)n_dom, rows, cols);
+        bit_reduce(rows, nr, c - s, Rr);            // hi in [1, 2^(c-1-s)]: c-s bits
+        bit_reduce(cols, nc, s, Rc);                // lo in [1, 2^s - 1]: s bits
+        k_join_rowcol<F><<<(unsigned)((n_dom + 63) / 64), 64, 0, st>>>(Rr, Rc, s, (int)n_dom, R);
+    } else if (tables) {
+        bit_reduce(buckets, nbins, n_bits, R);
     } else {
-        k_finish_bits<F><<<(unsigned)((n_dom * 32 + RED_T - 1) / RED_T), RED_T, sm_warp, st>>>(X, n_bits, (int)n_dom, R + 1);
+        bit_reduce(buckets, nbins, n_bits, R + 1);
         k_horner_windows<F><<<1, 32, 0, st>>>(R + 1, W, c, R);
     }
     ZK_CUDA(cudaGetLastError());
