@@ -151,6 +151,9 @@ __global__ void __launch_bounds__(64) k_finish_proofs(const G1XYZZ *__restrict__
 }
 }  // namespace
 
+// batches larger than PROVE_CHUNK are processed in slices (device workspace and the 31-bit MSM entry index bound the slice)
+static const size_t PROVE_CHUNK = 256;
+
 static int prove_impl(zk_ctx *ctx, const zk_params *p, size_t batch,
                       const uint64_t *a_ev, const uint64_t *b_ev, const uint64_t *c_ev, size_t n_c,
                       const uint64_t *inputs, size_t n_in, const uint64_t *aux, size_t n_aux,
@@ -164,7 +167,7 @@ static int prove_impl(zk_ctx *ctx, const zk_params *p, size_t batch,
     if (!ctx || !p || (!r1cs && (!a_ev || !b_ev || !c_ev)) || !inputs || !aux || !a_aux_d || !b_in_d || !b_aux_d || !r || !s || !proofs_out) {
         zk_set_error("zk_groth16_prove: NULL argument"); return ZK_ERR_INVALID;
     }
-    if (batch == 0 || batch > 4096 || n_c == 0) { zk_set_error("zk_groth16_prove: bad batch / constraint count"); return ZK_ERR_INVALID; }
+    if (batch == 0 || batch > PROVE_CHUNK || n_c == 0) { zk_set_error("zk_groth16_prove: bad batch / constraint count"); return ZK_ERR_INVALID; }
     if (p->device != ctx->device) { zk_set_error("params live on device %d, context on %d", p->device, ctx->device); return ZK_ERR_INVALID; }
     ZK_TRY(zk_use_device(ctx));
     cudaStream_t st = ctx->stream;
@@ -266,7 +269,14 @@ extern "C" int zk_groth16_prove_batch(zk_ctx *ctx, const zk_params *p, size_t ba
                                       const uint64_t *inputs, size_t n_in, const uint64_t *aux, size_t n_aux,
                                       const uint8_t *d1, const uint8_t *d2, const uint8_t *d3,
                                       const uint64_t *r, const uint64_t *s, uint8_t *out) {
-    return prove_impl(ctx, p, batch, a, b, c, n_c, inputs, n_in, aux, n_aux, d1, d2, d3, r, s, out);
+    if (!a || !b || !c || !inputs || !aux || !r || !s || !out) { zk_set_error("zk_groth16_prove_batch: NULL argument"); return ZK_ERR_INVALID; }
+    if (batch == 0) { zk_set_error("zk_groth16_prove_batch: empty batch"); return ZK_ERR_INVALID; }
+    for (size_t o = 0; o < batch; o += PROVE_CHUNK) {
+        size_t k = batch - o < PROVE_CHUNK ? batch - o : PROVE_CHUNK;
+        ZK_TRY(prove_impl(ctx, p, k, a + o * n_c * 4, b + o * n_c * 4, c + o * n_c * 4, n_c, inputs + o * n_in * 4, n_in, aux + o * n_aux * 4, n_aux,
+                          d1, d2, d3, r + o * 4, s + o * 4, out + o * 192));
+    }
+    return ZK_OK;
 }
 extern "C" int zk_groth16_prove(zk_ctx *ctx, const zk_params *p,
                                 const uint64_t *a, const uint64_t *b, const uint64_t *c, size_t n_c,
@@ -326,5 +336,11 @@ extern "C" int zk_groth16_prove_witness_batch(zk_ctx *ctx, const zk_params *p, c
                                               const uint64_t *inputs, const uint64_t *aux, const uint64_t *r, const uint64_t *s, uint8_t *proofs_out) {
     if (!q) { zk_set_error("zk_groth16_prove_witness_batch: NULL constraint system"); return ZK_ERR_INVALID; }
     if (q->device != ctx->device) { zk_set_error("constraint system lives on device %d, context on %d", q->device, ctx->device); return ZK_ERR_INVALID; }
-    return prove_impl(ctx, p, batch, nullptr, nullptr, nullptr, 0, inputs, q->n_in, aux, q->n_aux, nullptr, nullptr, nullptr, r, s, proofs_out, q);
+    if (!inputs || !aux || !r || !s || !proofs_out || batch == 0) { zk_set_error("zk_groth16_prove_witness_batch: bad argument"); return ZK_ERR_INVALID; }
+    for (size_t o = 0; o < batch; o += PROVE_CHUNK) {
+        size_t k = batch - o < PROVE_CHUNK ? batch - o : PROVE_CHUNK;
+        ZK_TRY(prove_impl(ctx, p, k, nullptr, nullptr, nullptr, 0, inputs + o * q->n_in * 4, q->n_in, aux + o * q->n_aux * 4, q->n_aux, nullptr, nullptr, nullptr,
+                          r + o * 4, s + o * 4, proofs_out + o * 192, q));
+    }
+    return ZK_OK;
 }

@@ -84,11 +84,22 @@ __global__ void k_ntt_tables(Fr *W, Fr *G, Fr *GI, Fr *consts, unsigned log_n) {
 
 __device__ __forceinline__ unsigned bitrev(unsigned x, int bits) { return bits ? (__brev(x) >> (32 - bits)) : 0; }
 
+// Geometry of one pass.  A "sub-array" is a contiguous run of 2^log_sub elements transformed on its own
+// (the whole vector for sizes <= 2^22; one row of 2^22 for larger sizes, whose root is w_N^(2^tw_shift)).
+struct PassGeom {
+    unsigned log_n;      // size of the whole transform (table index space)
+    unsigned log_sub;    // size of the sub-array this pass works in
+    int l1;              // columns pass: log of the column length; rows pass: log of the number of rows in the sub-array
+    int tw_shift;        // log_n - log_sub: sub-array twiddles are table entries scaled by 2^tw_shift
+    int y_is_row;        // blockIdx.y selects a row of the outer split (1) or a batch item (0)
+    int out_shift;       // rows pass with y_is_row: global out index = blockIdx.y + (o_sub << out_shift)
+};
+
 // In-place decimation-in-frequency transform of `cnt` independent tiles of 2^lb points held in
 // shared memory (tile t at sm + t * 2^lb).  Twiddle for the butterfly (i, i+h) of a 2h-group is
-// w_N^(j * N/(2h)), j = i mod h; inverse transforms index the table from the other end.
-__device__ __forceinline__ void smem_dif(Fr *sm, int lb, int cnt, const Fr *__restrict__ W, unsigned log_n, bool inverse) {
-    const unsigned n_mask = (1u << log_n) - 1;
+// w_sub^(j * sub/(2h)), j = i mod h; inverse transforms index the table from the other end.
+__device__ __forceinline__ void smem_dif(Fr *sm, int lb, int cnt, const Fr *__restrict__ W, const PassGeom &g, bool inverse) {
+    const unsigned n_mask = g.log_n >= 32 ? 0xffffffffu : ((1u << g.log_n) - 1);
     const int half_total = (cnt << lb) >> 1;
     for (int s = lb - 1; s >= 0; s--) {
         const int h = 1 << s;
@@ -97,7 +108,7 @@ __device__ __forceinline__ void smem_dif(Fr *sm, int lb, int cnt, const Fr *__re
             int j = q & (h - 1);
             int i = ((q >> s) << (s + 1)) | j;          // covers all tiles: tile size is a multiple of 2h
             Fr a = sm[i], b = sm[i + h];
-            unsigned e = (unsigned)j << (log_n - s - 1);
+            unsigned e = (unsigned)j << (g.log_n - s - 1);      // j * N / 2h  (independent of the sub-array size)
             if (inverse) e = (0u - e) & n_mask;
             Fr d = a - b;
             sm[i] = a + b;
@@ -107,49 +118,52 @@ __device__ __forceinline__ void smem_dif(Fr *sm, int lb, int cnt, const Fr *__re
     __syncthreads();
 }
 
-// pass A: columns.  data viewed as [N1][N2]; block handles `cols` adjacent columns.
-__global__ void __launch_bounds__(NTT_THREADS) k_ntt_cols(Fr *__restrict__ data, unsigned log_n, int l1, int cols_log,
+// columns pass over each sub-array viewed as [2^l1][2^(log_sub-l1)]; block handles 2^cols_log adjacent columns.
+__global__ void __launch_bounds__(NTT_THREADS) k_ntt_cols(const Fr *__restrict__ in, Fr *__restrict__ out, PassGeom g, int cols_log,
                                                           const Fr *__restrict__ W, const Fr *__restrict__ G, int coset_in, int inverse) {
-    extern __shared__ unsigned char smraw[];
+    extern __shared__ __align__(128) unsigned char smraw[];
     Fr *sm = reinterpret_cast<Fr *>(smraw);
-    const int l2 = log_n - l1, N1 = 1 << l1, cols = 1 << cols_log;
+    const int l1 = g.l1, l2 = g.log_sub - l1, N1 = 1 << l1, cols = 1 << cols_log;
     const size_t N2 = (size_t)1 << l2;
-    Fr *x = data + ((size_t)blockIdx.y << log_n);
+    const size_t base = (size_t)blockIdx.y << g.log_sub;
+    const Fr *x = in + base;
+    Fr *y = out + base;
     const size_t c0 = (size_t)blockIdx.x << cols_log;
     const int total = N1 << cols_log;
-    const unsigned n_mask = (1u << log_n) - 1;
+    const unsigned n_mask = g.log_n >= 32 ? 0xffffffffu : ((1u << g.log_n) - 1);
     // load: consecutive threads take consecutive columns of one row (cols*32 B contiguous); tile layout [col][n1]
     for (int q = threadIdx.x; q < total; q += NTT_THREADS) {
         int col = q & (cols - 1), n1 = q >> cols_log;
         size_t idx = (size_t)n1 * N2 + c0 + col;
         Fr v = load_fr(x + idx);
-        if (coset_in) v = v * load_fr(G + idx);
+        if (coset_in) v = v * load_fr(G + idx);             // coset scaling only where the sub-array is the whole transform
         sm[(col << l1) + n1] = v;
     }
-    smem_dif(sm, l1, cols, W, log_n, inverse != 0);
-    // store: frequency m1 sits at position bitrev(m1); multiply by the four-step twiddle w^(n2*m1)
+    smem_dif(sm, l1, cols, W, g, inverse != 0);
+    // store: frequency m1 sits at position bitrev(m1); multiply by the four-step twiddle w_sub^(n2*m1)
     for (int q = threadIdx.x; q < total; q += NTT_THREADS) {
         int col = q & (cols - 1), m1 = q >> cols_log;
         size_t n2 = c0 + col;
         Fr v = sm[(col << l1) + bitrev(m1, l1)];
-        unsigned e = (unsigned)((n2 * (size_t)m1) & n_mask);
+        unsigned e = (unsigned)(((n2 * (size_t)m1) << g.tw_shift) & n_mask);
         if (inverse) e = (0u - e) & n_mask;
         if (e) v = v * load_fr(W + e);
-        store_fr(x + (size_t)m1 * N2 + n2, v);
+        store_fr(y + (size_t)m1 * N2 + n2, v);
     }
 }
 
-// pass B: rows.  in viewed as [N1][N2]; block handles `rows` adjacent rows; out[m1 + N1*m2].
-// post: 0 none, 1 multiply by consts[0] (m^-1), 2 multiply by GI[out index] (g^-i m^-1)
-__global__ void __launch_bounds__(NTT_THREADS) k_ntt_rows(const Fr *__restrict__ in, Fr *__restrict__ out, unsigned log_n, int l1, int rows_log,
+// rows pass: each sub-array viewed as [2^l1][2^(log_sub-l1)]; block handles 2^rows_log adjacent rows; frequency
+// (m1, m2) goes to sub-array index m1 + 2^l1 * m2, i.e. the transposed position that makes the output natural order.
+// post: 0 none, 1 multiply by consts[0] (m^-1), 2 multiply by GI[global out index] (g^-i m^-1)
+__global__ void __launch_bounds__(NTT_THREADS) k_ntt_rows(const Fr *__restrict__ in, Fr *__restrict__ out, PassGeom g, int rows_log,
                                                           const Fr *__restrict__ W, const Fr *__restrict__ G, const Fr *__restrict__ GI,
                                                           const Fr *__restrict__ consts, int coset_in, int inverse, int post) {
     extern __shared__ __align__(128) unsigned char smraw[];
     Fr *sm = reinterpret_cast<Fr *>(smraw);
-    const int l2 = log_n - l1, N2 = 1 << l2, rows = 1 << rows_log;
+    const int l1 = g.l1, l2 = g.log_sub - l1, N2 = 1 << l2, rows = 1 << rows_log;
     const size_t N1 = (size_t)1 << l1;
-    const Fr *x = in + ((size_t)blockIdx.y << log_n);
-    Fr *y = out + ((size_t)blockIdx.y << log_n);
+    const size_t base = (size_t)blockIdx.y << g.log_sub;
+    const Fr *x = in + base;
     const size_t r0 = (size_t)blockIdx.x << rows_log;
     const int total = N2 << rows_log;
     if (!coset_in) {
@@ -166,21 +180,22 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_rows(const Fr *__restrict__
         }
         zktma::mbar_wait(&bar, 0);
     } else {
-        for (int q = threadIdx.x; q < total; q += NTT_THREADS) {     // coset scaling on load (only when there is no pass A)
+        for (int q = threadIdx.x; q < total; q += NTT_THREADS) {     // coset scaling on load (only when there is no columns pass)
             size_t idx = (r0 << l2) + q;
             sm[q] = load_fr(x + idx) * load_fr(G + idx);
         }
     }
-    smem_dif(sm, l2, rows, W, log_n, inverse != 0);
+    smem_dif(sm, l2, rows, W, g, inverse != 0);
     Fr scale = Fr::one();
     if (post == 1) scale = load_fr(consts);
     for (int q = threadIdx.x; q < total; q += NTT_THREADS) {     // consecutive threads: consecutive m1 of one m2
         int row = q & (rows - 1), m2 = q >> rows_log;
         Fr v = sm[(row << l2) + bitrev(m2, l2)];
-        size_t o = (r0 + row) + N1 * (size_t)m2;
+        size_t o_sub = (r0 + row) + N1 * (size_t)m2;
+        size_t o = g.y_is_row ? (size_t)blockIdx.y + (o_sub << g.out_shift) : base + o_sub;
         if (post == 1) v = v * scale;
-        else if (post == 2) v = v * load_fr(GI + o);
-        store_fr(y + o, v);
+        else if (post == 2) v = v * load_fr(GI + (g.y_is_row ? o : o_sub));   // table index = position inside the transform
+        store_fr(out + o, v);
     }
 }
 
@@ -208,38 +223,64 @@ static int get_tables(zk_ctx *ctx, unsigned log_n, NttTables **out) {
 }
 
 // `batch` transforms of 2^log_n contiguous elements each, in place in d_data.
+//   log_n <= 11          one rows pass, the whole vector in one shared-memory tile (in place)
+//   12 <= log_n <= 22    columns pass data -> tmp, rows pass tmp -> data
+//   log_n > 22           outer split N = 2^(log_n-22) x 2^22: columns pass over the outer dimension, then every 2^22 row
+//                        gets the two passes above with the root w^(2^(log_n-22)) and a transposed final store (batch == 1)
 int zk_ntt_run(zk_ctx *ctx, void *d_data, unsigned log_n, int mode, size_t batch) {
     if (log_n > 32) { zk_set_error("PolynomialDegreeTooLarge: log_n = %u", log_n); return ZK_ERR_POLY_DEGREE_TOO_LARGE; }
-    if (log_n > 2 * MAX_TILE_LOG) { zk_set_error("NTT sizes above 2^%d are not implemented", 2 * MAX_TILE_LOG); return ZK_ERR_INVALID; }
+    if (log_n > 28) { zk_set_error("NTT sizes above 2^28 are not supported by this build (twiddle tables would need %llu GB)", (unsigned long long)(96ull << (log_n - 30))); return ZK_ERR_INVALID; }
     if (mode < 0 || mode > 3 || batch == 0 || batch > 65535) { zk_set_error("zk_ntt: bad mode/batch"); return ZK_ERR_INVALID; }
+    if (log_n > 2 * MAX_TILE_LOG && batch != 1) { zk_set_error("batched NTTs above 2^22 are not supported"); return ZK_ERR_INVALID; }
     ZK_TRY(zk_use_device(ctx));
     if (log_n == 0) return ZK_OK;     // size-1 transform is the identity (m^-1 = 1)
     NttTables *t;
     ZK_TRY(get_tables(ctx, log_n, &t));
     const size_t n = (size_t)1 << log_n;
-    ZK_TRY(ctx->ntt_tmp.reserve(n * 32 * batch));
     const int inverse = (mode == ZK_NTT_IFFT || mode == ZK_NTT_ICOSET_FFT);
     const int coset_in = (mode == ZK_NTT_COSET_FFT);
     const int post = mode == ZK_NTT_IFFT ? 1 : (mode == ZK_NTT_ICOSET_FFT ? 2 : 0);
-    const int l1 = log_n > MAX_TILE_LOG ? (int)log_n / 2 : 0, l2 = (int)log_n - l1;
     static bool attr_done = false;
     if (!attr_done) {
         ZK_CUDA(cudaFuncSetAttribute(k_ntt_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << MAX_TILE_LOG));
         ZK_CUDA(cudaFuncSetAttribute(k_ntt_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << MAX_TILE_LOG));
         attr_done = true;
     }
-    Fr *data = (Fr *)d_data, *tmp = ctx->ntt_tmp.as<Fr>();
-    if (l1 > 0) {
-        int cols_log = MAX_TILE_LOG - l1; if (cols_log > l2) cols_log = l2;
-        dim3 g((unsigned)(n >> (l1 + cols_log)), (unsigned)batch);
-        k_ntt_cols<<<g, NTT_THREADS, (size_t)32 << (l1 + cols_log), ctx->stream>>>(data, log_n, l1, cols_log, t->w.as<Fr>(), t->g.as<Fr>(), coset_in, inverse);
+    Fr *data = (Fr *)d_data;
+    const Fr *W = t->w.as<Fr>(), *G = t->g.as<Fr>(), *GI = t->gi.as<Fr>(), *consts = t->consts.as<Fr>();
+    cudaStream_t st = ctx->stream;
+    auto cols = [&](const Fr *in, Fr *out, PassGeom g, unsigned by, int cin) {
+        int l2 = (int)g.log_sub - g.l1;
+        int cols_log = MAX_TILE_LOG - g.l1; if (cols_log > l2) cols_log = l2;
+        dim3 grid((unsigned)(((size_t)1 << g.log_sub) >> (g.l1 + cols_log)), by);
+        k_ntt_cols<<<grid, NTT_THREADS, (size_t)32 << (g.l1 + cols_log), st>>>(in, out, g, cols_log, W, G, cin, inverse);
+    };
+    auto rows = [&](const Fr *in, Fr *out, PassGeom g, unsigned by, int cin, int pst) {
+        int l2 = (int)g.log_sub - g.l1;
+        int rows_log = MAX_TILE_LOG - l2; if (rows_log > g.l1) rows_log = g.l1;
+        dim3 grid((unsigned)(((size_t)1 << g.log_sub) >> (l2 + rows_log)), by);
+        k_ntt_rows<<<grid, NTT_THREADS, (size_t)32 << (l2 + rows_log), st>>>(in, out, g, rows_log, W, G, GI, consts, cin, inverse, pst);
+    };
+    if (log_n <= (unsigned)MAX_TILE_LOG) {
+        PassGeom g{log_n, log_n, 0, 0, 0, 0};
+        rows(data, data, g, (unsigned)batch, coset_in, post);              // whole vector in one tile: in place is safe
+    } else if (log_n <= 2 * (unsigned)MAX_TILE_LOG) {
+        ZK_TRY(ctx->ntt_tmp.reserve(n * 32 * batch));
+        Fr *tmp = ctx->ntt_tmp.as<Fr>();
+        PassGeom g{log_n, log_n, (int)log_n / 2, 0, 0, 0};
+        cols(data, tmp, g, (unsigned)batch, coset_in);
+        rows(tmp, data, g, (unsigned)batch, 0, post);
+    } else {
+        ZK_TRY(ctx->ntt_tmp.reserve(n * 32));
+        Fr *tmp = ctx->ntt_tmp.as<Fr>();
+        const int l0 = (int)log_n - 2 * MAX_TILE_LOG;                       // outer dimension 2^l0 <= 2^10
+        PassGeom g0{log_n, log_n, l0, 0, 0, 0};
+        cols(data, tmp, g0, 1, coset_in);                                   // outer columns, twiddle w^(n' m0)
+        PassGeom g1{log_n, 2 * MAX_TILE_LOG, MAX_TILE_LOG, l0, 1, l0};
+        cols(tmp, tmp, g1, 1u << l0, 0);                                    // every row: inner columns (in place)
+        rows(tmp, data, g1, 1u << l0, 0, post);                             // every row: inner rows, store at m0 + 2^l0 * m'
     }
-    int rows_log = MAX_TILE_LOG - l2; if (rows_log > l1) rows_log = l1;
-    dim3 g((unsigned)(n >> (l2 + rows_log)), (unsigned)batch);
-    k_ntt_rows<<<g, NTT_THREADS, (size_t)32 << (l2 + rows_log), ctx->stream>>>(data, tmp, log_n, l1, rows_log, t->w.as<Fr>(), t->g.as<Fr>(), t->gi.as<Fr>(),
-                                                                             t->consts.as<Fr>(), l1 == 0 ? coset_in : 0, inverse, post);
     ZK_CUDA(cudaGetLastError());
-    ZK_CUDA(cudaMemcpyAsync(data, tmp, n * 32 * batch, cudaMemcpyDeviceToDevice, ctx->stream));
     return ZK_OK;
 }
 
