@@ -9,7 +9,7 @@
 namespace zkmsm {
 
 constexpr int TASK_LEN_MAX = 64;          // target upper bound of mixed additions per accumulate task
-constexpr int TASK_LEN_MIN = 4;
+constexpr int TASK_LEN_MIN = 16;         // shorter tasks make the per-bucket combine (serial point additions) the bottleneck of small MSMs
 constexpr uint32_t TARGET_TASKS = 148u * 1024u;   // aim for >= ~1k resident tasks per SM so small / skewed MSMs still fill the GPU
 
 template <class F>
