@@ -194,6 +194,9 @@ static int prove_impl(zk_ctx *ctx, const zk_params *p, size_t batch,
     ZK_TRY(ctx->g_c.reserve(batch * (n_in + n_aux) * 32 + 64));      // inputs | aux (canonical)
     size_t max_scal = nH; if (nA > max_scal) max_scal = nA; if (nB > max_scal) max_scal = nB;
     ZK_TRY(ctx->g_scal.reserve(batch * max_scal * 32));
+    ZK_TRY(ctx->g_scal2.reserve(batch * nB * 32));
+    if (!ctx->aux) ZK_TRY(zk_ctx_create(ctx->device, nullptr, &ctx->aux));      // second lane for the G2 MSM
+    zk_ctx *lane2 = ctx->aux;
     auto rnd = [](size_t b) { return (b + 255) & ~(size_t)255; };
     size_t misc_bytes = rnd(a_idx.size() * 4 + 4) + rnd(bi_idx.size() * 4 + 4) + rnd(ba_idx.size() * 4 + 4) + 2 * rnd(batch * 32) + rnd(batch * 128) +
                         4 * rnd(batch * sizeof(G1XYZZ)) + rnd(2 * batch * sizeof(G1XYZZ)) + rnd(batch * sizeof(G2XYZZ)) + rnd(batch * 192);
@@ -216,6 +219,22 @@ static int prove_impl(zk_ctx *ctx, const zk_params *p, size_t batch,
     uint4 *d_in = ctx->g_c.as<uint4>(), *d_aux = d_in + batch * n_in * 2;
     ZK_CUDA(cudaMemcpyAsync(d_in, inputs, batch * n_in * 32, cudaMemcpyHostToDevice, st));
     ZK_CUDA(cudaMemcpyAsync(d_aux, aux, batch * n_aux * 32, cudaMemcpyHostToDevice, st));
+    // B-query scalars (inputs|B ++ aux|B ++ [1, s]) depend only on the assignment: build them first and start the G2 MSM
+    // on the second lane, so its latency-bound tail overlaps the NTTs and the G1 MSMs of this lane.
+    uint4 *scal2 = ctx->g_scal2.as<uint4>();
+    if (bi_idx.size()) k_gather32<<<dim3((unsigned)((bi_idx.size() + 255) / 256), (unsigned)batch), 256, 0, st>>>(d_in, n_in, d_biidx, bi_idx.size(), scal2, nB, 0);
+    if (ba_idx.size()) k_gather32<<<dim3((unsigned)((ba_idx.size() + 255) / 256), (unsigned)batch), 256, 0, st>>>(d_aux, n_aux, d_baidx, ba_idx.size(), scal2, nB, bi_idx.size());
+    k_put_terms<<<(unsigned)((batch + 63) / 64), 64, 0, st>>>((const uint4 *)d_terms, 0, 2, 2, scal2, nB, nB - 2, batch);
+    cudaEvent_t ev_b = nullptr, ev_g2 = nullptr;
+    ZK_CUDA(cudaEventCreateWithFlags(&ev_b, cudaEventDisableTiming));
+    ZK_CUDA(cudaEventCreateWithFlags(&ev_g2, cudaEventDisableTiming));
+    ZK_CUDA(cudaEventRecord(ev_b, st));
+    ZK_CUDA(cudaStreamWaitEvent(lane2->stream, ev_b, 0));
+    int rc2 = zk_msm_run(lane2, p->b2, scal2, nB, batch);
+    if (rc2 == ZK_OK) {
+        cudaMemcpyAsync(d_gb, lane2->result.p, batch * sizeof(G2XYZZ), cudaMemcpyDeviceToDevice, lane2->stream);
+        cudaEventRecord(ev_g2, lane2->stream);
+    } else { cudaEventDestroy(ev_b); cudaEventDestroy(ev_g2); return rc2; }
     if (r1cs) {
         ZK_TRY(ctx->g_b.reserve(batch * (n_in + n_aux) * 32));       // z in Montgomery form
         ZK_TRY(zk_fr_witness_to_mont(ctx, d_in, n_in, d_aux, n_aux, batch, ctx->g_b.p));
@@ -248,20 +267,19 @@ static int prove_impl(zk_ctx *ctx, const zk_params *p, size_t batch,
     k_put_terms<<<(unsigned)((batch + 63) / 64), 64, 0, st>>>((const uint4 *)d_terms, 0, 1, 2, scal, nA, nA - 2, batch);
     ZK_TRY(zk_msm_run(ctx, p->a, scal, nA, batch));
     ZK_CUDA(cudaMemcpyAsync(d_ga, ctx->result.p, batch * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, st));
-    // g_b1 / g_b: inputs|B ++ aux|B ++ [1, s]
-    if (bi_idx.size()) k_gather32<<<dim3((unsigned)((bi_idx.size() + 255) / 256), (unsigned)batch), 256, 0, st>>>(d_in, n_in, d_biidx, bi_idx.size(), scal, nB, 0);
-    if (ba_idx.size()) k_gather32<<<dim3((unsigned)((ba_idx.size() + 255) / 256), (unsigned)batch), 256, 0, st>>>(d_aux, n_aux, d_baidx, ba_idx.size(), scal, nB, bi_idx.size());
-    k_put_terms<<<(unsigned)((batch + 63) / 64), 64, 0, st>>>((const uint4 *)d_terms, 0, 2, 2, scal, nB, nB - 2, batch);
-    ZK_TRY(zk_msm_run(ctx, p->b1, scal, nB, batch));
+    // g_b1 (this lane; g_b is already running on the second lane with the same scalars)
+    ZK_TRY(zk_msm_run(ctx, p->b1, scal2, nB, batch));
     ZK_CUDA(cudaMemcpyAsync(d_gb1, ctx->result.p, batch * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, st));
-    ZK_TRY(zk_msm_run(ctx, p->b2, scal, nB, batch));
-    ZK_CUDA(cudaMemcpyAsync(d_gb, ctx->result.p, batch * sizeof(G2XYZZ), cudaMemcpyDeviceToDevice, st));
+    ZK_CUDA(cudaStreamWaitEvent(st, ev_g2, 0));                       // join: g_b (G2) is ready in d_gb
     // ---- assembly + Proof::write ----
     k_scale_points<<<(unsigned)((2 * batch + 63) / 64), 64, 0, st>>>(d_ga, d_gb1, (const uint32_t *)d_terms, batch, d_T);
     k_finish_proofs<<<(unsigned)((batch + 63) / 64), 64, 0, st>>>(d_ga, d_gb, d_T, d_H, d_L, batch, d_proofs);
     ZK_CUDA(cudaGetLastError());
     ZK_CUDA(cudaMemcpyAsync(proofs_out, d_proofs, batch * 192, cudaMemcpyDeviceToHost, st));
-    return zk_check_err_flag(ctx);      // synchronises; reports non-canonical scalars
+    int rc = zk_check_err_flag(ctx);    // synchronises this lane (which has joined the second); reports non-canonical scalars
+    int rcb = zk_check_err_flag(lane2);
+    cudaEventDestroy(ev_b); cudaEventDestroy(ev_g2);
+    return rc ? rc : rcb;
 }
 
 extern "C" int zk_groth16_prove_batch(zk_ctx *ctx, const zk_params *p, size_t batch,
