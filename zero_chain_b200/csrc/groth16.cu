@@ -197,6 +197,9 @@ static int prove_impl(zk_ctx *ctx, const zk_params *p, size_t batch,
     ZK_TRY(ctx->g_scal2.reserve(batch * nB * 32));
     if (!ctx->aux) ZK_TRY(zk_ctx_create(ctx->device, nullptr, &ctx->aux));      // second lane for the G2 MSM
     zk_ctx *lane2 = ctx->aux;
+    ZK_TRY(ctx->g_scal3.reserve(batch * nA * 32));
+    if (!ctx->aux2) ZK_TRY(zk_ctx_create(ctx->device, nullptr, &ctx->aux2));    // third lane for the A and B1 MSMs
+    zk_ctx *lane3 = ctx->aux2;
     auto rnd = [](size_t b) { return (b + 255) & ~(size_t)255; };
     size_t misc_bytes = rnd(a_idx.size() * 4 + 4) + rnd(bi_idx.size() * 4 + 4) + rnd(ba_idx.size() * 4 + 4) + 2 * rnd(batch * 32) + rnd(batch * 128) +
                         4 * rnd(batch * sizeof(G1XYZZ)) + rnd(2 * batch * sizeof(G1XYZZ)) + rnd(batch * sizeof(G2XYZZ)) + rnd(batch * 192);
@@ -235,6 +238,25 @@ static int prove_impl(zk_ctx *ctx, const zk_params *p, size_t batch,
         cudaMemcpyAsync(d_gb, lane2->result.p, batch * sizeof(G2XYZZ), cudaMemcpyDeviceToDevice, lane2->stream);
         cudaEventRecord(ev_g2, lane2->stream);
     } else { cudaEventDestroy(ev_b); cudaEventDestroy(ev_g2); return rc2; }
+    // third lane: g_a = MSM(a', inputs ++ aux|A ++ [1, r]) and g_b1 = MSM(b_g1', B scalars) need only the assignment too
+    uint4 *scal3 = ctx->g_scal3.as<uint4>();
+    ZK_CUDA(cudaMemcpy2DAsync(scal3, nA * 32, d_in, n_in * 32, n_in * 32, batch, cudaMemcpyDeviceToDevice, st));
+    if (a_idx.size()) k_gather32<<<dim3((unsigned)((a_idx.size() + 255) / 256), (unsigned)batch), 256, 0, st>>>(d_aux, n_aux, d_aidx, a_idx.size(), scal3, nA, n_in);
+    k_put_terms<<<(unsigned)((batch + 63) / 64), 64, 0, st>>>((const uint4 *)d_terms, 0, 1, 2, scal3, nA, nA - 2, batch);
+    cudaEvent_t ev_a = nullptr, ev_l3 = nullptr;
+    ZK_CUDA(cudaEventCreateWithFlags(&ev_a, cudaEventDisableTiming));
+    ZK_CUDA(cudaEventCreateWithFlags(&ev_l3, cudaEventDisableTiming));
+    ZK_CUDA(cudaEventRecord(ev_a, st));
+    ZK_CUDA(cudaStreamWaitEvent(lane3->stream, ev_a, 0));
+    int rc3 = zk_msm_run(lane3, p->a, scal3, nA, batch);
+    if (rc3 == ZK_OK) {
+        cudaMemcpyAsync(d_ga, lane3->result.p, batch * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, lane3->stream);
+        rc3 = zk_msm_run(lane3, p->b1, scal2, nB, batch);
+    }
+    if (rc3 == ZK_OK) {
+        cudaMemcpyAsync(d_gb1, lane3->result.p, batch * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, lane3->stream);
+        cudaEventRecord(ev_l3, lane3->stream);
+    } else { cudaEventDestroy(ev_b); cudaEventDestroy(ev_g2); cudaEventDestroy(ev_a); cudaEventDestroy(ev_l3); return rc3; }
     if (r1cs) {
         ZK_TRY(ctx->g_b.reserve(batch * (n_in + n_aux) * 32));       // z in Montgomery form
         ZK_TRY(zk_fr_witness_to_mont(ctx, d_in, n_in, d_aux, n_aux, batch, ctx->g_b.p));
@@ -261,15 +283,7 @@ static int prove_impl(zk_ctx *ctx, const zk_params *p, size_t batch,
     // L
     ZK_TRY(zk_msm_run(ctx, p->l, d_aux, n_aux, batch));
     ZK_CUDA(cudaMemcpyAsync(d_L, ctx->result.p, batch * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, st));
-    // g_a: inputs ++ aux|A ++ [1, r]
-    ZK_CUDA(cudaMemcpy2DAsync(scal, nA * 32, d_in, n_in * 32, n_in * 32, batch, cudaMemcpyDeviceToDevice, st));
-    if (a_idx.size()) k_gather32<<<dim3((unsigned)((a_idx.size() + 255) / 256), (unsigned)batch), 256, 0, st>>>(d_aux, n_aux, d_aidx, a_idx.size(), scal, nA, n_in);
-    k_put_terms<<<(unsigned)((batch + 63) / 64), 64, 0, st>>>((const uint4 *)d_terms, 0, 1, 2, scal, nA, nA - 2, batch);
-    ZK_TRY(zk_msm_run(ctx, p->a, scal, nA, batch));
-    ZK_CUDA(cudaMemcpyAsync(d_ga, ctx->result.p, batch * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, st));
-    // g_b1 (this lane; g_b is already running on the second lane with the same scalars)
-    ZK_TRY(zk_msm_run(ctx, p->b1, scal2, nB, batch));
-    ZK_CUDA(cudaMemcpyAsync(d_gb1, ctx->result.p, batch * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, st));
+    ZK_CUDA(cudaStreamWaitEvent(st, ev_l3, 0));                       // join: g_a, g_b1 from the third lane
     ZK_CUDA(cudaStreamWaitEvent(st, ev_g2, 0));                       // join: g_b (G2) is ready in d_gb
     // ---- assembly + Proof::write ----
     k_scale_points<<<(unsigned)((2 * batch + 63) / 64), 64, 0, st>>>(d_ga, d_gb1, (const uint32_t *)d_terms, batch, d_T);
@@ -277,9 +291,9 @@ static int prove_impl(zk_ctx *ctx, const zk_params *p, size_t batch,
     ZK_CUDA(cudaGetLastError());
     ZK_CUDA(cudaMemcpyAsync(proofs_out, d_proofs, batch * 192, cudaMemcpyDeviceToHost, st));
     int rc = zk_check_err_flag(ctx);    // synchronises this lane (which has joined the second); reports non-canonical scalars
-    int rcb = zk_check_err_flag(lane2);
-    cudaEventDestroy(ev_b); cudaEventDestroy(ev_g2);
-    return rc ? rc : rcb;
+    int rcb = zk_check_err_flag(lane2), rcc = zk_check_err_flag(lane3);
+    cudaEventDestroy(ev_b); cudaEventDestroy(ev_g2); cudaEventDestroy(ev_a); cudaEventDestroy(ev_l3);
+    return rc ? rc : (rcb ? rcb : rcc);
 }
 
 extern "C" int zk_groth16_prove_batch(zk_ctx *ctx, const zk_params *p, size_t batch,
