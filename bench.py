@@ -350,9 +350,11 @@ def prove_metrics(ctx, zk, sy, args, batch=256, steps=3):
         raise SystemExit("PARITY FAILURE: witness-path proofs differ from the evaluation-path proofs")
     h2d_w = views[3].nbytes + views[4].nbytes + rs.nbytes + ss.nbytes
     cs.free()
-    t = time.perf_counter()
-    single = zk.create_proof_batch_raw(params, 1, *[v[:1] for v in views], *dens, rs[:1], ss[:1])
-    lat = time.perf_counter() - t
+    lat = 1e9
+    for _ in range(4):                   # first call loads the single-domain kernels lazily; report the steady-state latency
+        t = time.perf_counter()
+        single = zk.create_proof_batch_raw(params, 1, *[v[:1] for v in views], *dens, rs[:1], ss[:1])
+        lat = min(lat, time.perf_counter() - t)
     assert single == proofs[:192]
     # CPU port of the reference path on the same CRS / witness
     op = co.Params(crs.params_bytes, checked=False)
