@@ -32,8 +32,9 @@ sys.path.insert(0, ROOT)
 
 LOG_N = 20
 N_SETS = 8                     # distinct scalar vectors cycled through: 8 x 32 MiB = 256 MiB > 126 MB L2
-KERNELS_PER_MSM = 17           # digits, tile_hist, col_scan, 2 x (scan_block, scan_block, scan_add), scatter,
+KERNELS_PER_MSM = 18           # digits, tile_hist, col_scan, 2 x (scan_block, scan_block, scan_add), scatter, pick_task_len,
                                # accumulate, combine_serial, combine_warp, bit_sums, sum_points, finish_bits, encode
+                               # (counted from the ncu launch list profiles/r01_launches_msm_2p20.csv; N > 1 adds the fold kernel)
 ALGO_MODMUL_PER_TERM = 176     # 11 (mixed add) x ceil(255/16) windows — SURVEY.md §8(d) / BASELINE.md §3
 ALGO_BYTES_PER_TERM = 128      # 96 B base + 32 B scalar
 
@@ -266,7 +267,7 @@ def run_ours(args):
                        "setup_s_untimed": round(setup_s, 2)},
             "e2e": {"value": e2e_value, "unit": "Mop/s", "h2d_bytes_per_step": n * 32 * world, "d2h_bytes_per_step": 96 * world,
                     "ms_per_step": ms_e2e / args.steps, "api": "zk_msm (C ABI, scalars in pinned host memory)"},
-            "gpu_launches": KERNELS_PER_MSM * args.steps * world,
+            "gpu_launches": (KERNELS_PER_MSM + (1 if world > 1 else 0)) * args.steps * world,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
         }
         if args.secondary and world == 1:
