@@ -86,6 +86,18 @@ def test_msm_g1_vs_oracle(ctx, n, c, tables):
     b.free()
 
 
+@pytest.mark.parametrize("n,c", [(3000, 17), (40000, 18), (40000, 20)])
+def test_msm_wide_windows_two_level_sort(ctx, n, c):
+    """Windows above 16 bits use the two-level (coarse / fine) counting sort and the row/column bucket reduction."""
+    bases = co.g1_fixed_base(sy.random_fr_limbs(n, 3 * n + c))
+    scal = sy.random_fr_limbs(n, 3 * n + c + 1)
+    scal[:6] = co.ints_to_limbs([0, 1, pr.R - 1, 2, (1 << 255) % pr.R, pr.R - (1 << 128)], 4)
+    scal[100:200, :] = 0; scal[100:200, 0] = 1                       # a heavy bucket (all ones)
+    b = zk.Bases(ctx, 1, bases, window_bits=c, precompute=True)
+    assert zk.multiexp(b, scal) == _enc(1, co.g1_msm(bases, scal))
+    b.free()
+
+
 def test_msm_g1_closed_form_and_skew(ctx):
     # bases (i+1)*G => result (sum s_i (i+1)) G; witness-like scalars: mostly 0/1 (heavy buckets)
     n = 30000

@@ -48,7 +48,7 @@ extern "C" void zk_ctx_destroy(zk_ctx *c) {
     DevBuf *bufs[] = {&c->scalars, &c->digits, &c->tile_hist, &c->tile_off, &c->sizes, &c->bucket_off, &c->task_off, &c->scan_scratch,
                       &c->sorted, &c->partials, &c->buckets, &c->red_part, &c->red_x, &c->result, &c->out_bytes, &c->stage_a, &c->stage_b,
                       &c->stage_c, &c->ntt_tw, &c->ntt_tmp, &c->g_a, &c->g_b, &c->g_c, &c->g_h, &c->g_scal, &c->g_misc,
-                      &c->aff_pts0, &c->aff_pts1, &c->aff_scratch, &c->aff_off0, &c->aff_off1, &c->aff_sizes0, &c->aff_sizes1, &c->red_rows, &c->g_scal2, &c->g_scal3};
+                      &c->aff_pts0, &c->aff_pts1, &c->aff_scratch, &c->aff_off0, &c->aff_off1, &c->aff_sizes0, &c->aff_sizes1, &c->red_rows, &c->g_scal2, &c->g_scal3, &c->sorted2, &c->coarse_off, &c->coarse_sizes};
     for (DevBuf *b : bufs) b->release();
     if (c->d_err) cudaFree(c->d_err);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -95,7 +95,7 @@ int zk_bases_from_device(zk_ctx *ctx, int group, const void *d_points, size_t n,
     zk_bases *b = new zk_bases();
     b->group = group; b->device = ctx->device; b->n = n;
     b->c = window_bits > 0 ? window_bits : pick_window(n);
-    if (b->c < 2 || b->c > 16) { delete b; zk_set_error("window_bits must be in [2,16]"); return ZK_ERR_INVALID; }
+    if (b->c < 2 || b->c > 20 || (b->c > 16 && !precompute)) { delete b; zk_set_error("window_bits must be in [2,16] (17..20 with precomputed tables)"); return ZK_ERR_INVALID; }
     b->W = 255 / b->c + 1;
     b->tables = precompute != 0;
     size_t psz = group == 1 ? sizeof(G1Affine) : sizeof(G2Affine);

@@ -76,7 +76,8 @@ static __global__ void k_msm_digits(const uint32_t *__restrict__ scalars, uint32
 }
 
 // ---- 2. counting sort --------------------------------------------------------------------------
-static __global__ void __launch_bounds__(SORT_THREADS) k_tile_hist(const uint32_t *__restrict__ digits, uint64_t e_ws, int nbins,
+// `shift` > 0 bins by the high bits of the bucket key (coarse level of the two-level sort used for windows above 16 bits)
+static __global__ void __launch_bounds__(SORT_THREADS) k_tile_hist(const uint32_t *__restrict__ digits, uint64_t e_ws, int nbins, int shift,
                                                             uint32_t *__restrict__ tile_hist, int tiles_per_ws) {
     extern __shared__ uint32_t sh[];
     int tile = blockIdx.x, ws = blockIdx.y;
@@ -86,7 +87,7 @@ static __global__ void __launch_bounds__(SORT_THREADS) k_tile_hist(const uint32_
     const uint32_t *d = digits + (size_t)ws * e_ws;
     for (uint64_t p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
         uint32_t code = d[p];
-        if (code != DIGIT_ZERO) atomicAdd(&sh[code & 0x7fffffffu], 1u);
+        if (code != DIGIT_ZERO) atomicAdd(&sh[(code & 0x7fffffffu) >> shift], 1u);
     }
     __syncthreads();
     uint32_t *o = tile_hist + ((size_t)ws * tiles_per_ws + tile) * nbins;
@@ -107,7 +108,7 @@ static __global__ void k_col_scan(const uint32_t *__restrict__ tile_hist, uint32
     }
     sizes[g] = run;
 }
-static __global__ void __launch_bounds__(SORT_THREADS) k_scatter(const uint32_t *__restrict__ digits, uint64_t e_ws, int nbins,
+static __global__ void __launch_bounds__(SORT_THREADS) k_scatter(const uint32_t *__restrict__ digits, uint64_t e_ws, int nbins, int shift,
                                                           const uint32_t *__restrict__ tile_off, const uint32_t *__restrict__ bucket_off,
                                                           uint32_t *__restrict__ sorted, int tiles_per_ws) {
     extern __shared__ uint32_t sh[];
@@ -121,9 +122,59 @@ static __global__ void __launch_bounds__(SORT_THREADS) k_scatter(const uint32_t 
     for (uint64_t p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
         uint32_t code = d[p];
         if (code != DIGIT_ZERO) {
-            uint32_t pos = atomicAdd(&sh[code & 0x7fffffffu], 1u);
+            uint32_t pos = atomicAdd(&sh[(code & 0x7fffffffu) >> shift], 1u);
             sorted[pos] = (uint32_t)p | (code & 0x80000000u);
         }
+    }
+}
+
+// Fine level of the two-level sort (windows above 16 bits: 2^(c-1) buckets no longer fit a shared-memory histogram).
+// One block per (coarse bin, domain): the entries of the coarse bin (already contiguous) are counted by the low `low`
+// bits of their key in shared memory, the counts are scanned, and the entries are scattered to their final places.
+// Writes bucket sizes and bucket offsets directly (no global scan needed); the digit of an entry is re-read from the
+// digits array through its position.
+static __global__ void __launch_bounds__(1024) k_fine_sort(const uint32_t *__restrict__ coarse_sorted, const uint32_t *__restrict__ coarse_off,
+                                                          const uint32_t *__restrict__ digits, uint64_t e_ws, int n_coarse, int low,
+                                                          uint32_t *__restrict__ sizes, uint32_t *__restrict__ bucket_off, uint32_t *__restrict__ sorted) {
+    __shared__ uint32_t hist[1024];
+    __shared__ uint32_t wsum[32];
+    const int cb = blockIdx.x, dom = blockIdx.y, g = dom * n_coarse + cb;
+    const uint32_t r0 = coarse_off[g], r1 = coarse_off[g + 1], fmask = (1u << low) - 1u;
+    const uint32_t *d = digits + (size_t)dom * e_ws;
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t i = r0 + threadIdx.x; i < r1; i += blockDim.x) {
+        uint32_t code = coarse_sorted[i];
+        atomicAdd(&hist[d[code & 0x7fffffffu] & fmask], 1u);
+    }
+    __syncthreads();
+    // exclusive scan of the (<= 1024) counters: one per thread
+    uint32_t v = threadIdx.x < (1u << low) ? hist[threadIdx.x] : 0, inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if ((threadIdx.x & 31) >= (unsigned)o) inc += t; }
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t w = wsum[threadIdx.x], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, wi, o); if (threadIdx.x >= (unsigned)o) wi += t; }
+        wsum[threadIdx.x] = wi - w;
+    }
+    __syncthreads();
+    uint32_t excl = inc - v + wsum[threadIdx.x >> 5];
+    __syncthreads();
+    if (threadIdx.x < (1u << low)) {
+        size_t b = ((size_t)g << low) + threadIdx.x;
+        sizes[b] = v;
+        bucket_off[b] = r0 + excl;
+        hist[threadIdx.x] = r0 + excl;           // becomes the scatter cursor
+    }
+    if (cb == n_coarse - 1 && dom == (int)gridDim.y - 1 && threadIdx.x == 0) bucket_off[((size_t)g + 1) << low] = r1;
+    __syncthreads();
+    for (uint32_t i = r0 + threadIdx.x; i < r1; i += blockDim.x) {
+        uint32_t code = coarse_sorted[i];
+        uint32_t pos = atomicAdd(&hist[d[code & 0x7fffffffu] & fmask], 1u);
+        sorted[pos] = code;
     }
 }
 
@@ -325,15 +376,16 @@ __global__ void __launch_bounds__(RED_T) k_finish_bits(const XYZZ<F> *__restrict
 // EIGHT lanes per (domain, row hi = 1..N/S) or (domain, column lo = 1..S-1): each lane adds every 8th element serially,
 // then a 3-level tree inside the group (a full warp per row would spend most of its issue slots in the tree).
 // rows[dom][hi-1], cols[dom][lo-1].
-template <class F>
+// GL lanes per item: 8 for many domains (work-bound), 32 for one large domain (depth-bound: long rows).
+template <class F, int GL>
 __global__ void __launch_bounds__(RED_T) k_rowcol_sums(const XYZZ<F> *__restrict__ B, int N, int s, int n_dom,
                                                        XYZZ<F> *__restrict__ rows, XYZZ<F> *__restrict__ cols) {
     extern __shared__ unsigned char smraw[];
-    const uint32_t lane = threadIdx.x & 31, sub = lane & 7;
+    const uint32_t lane = threadIdx.x & 31, sub = lane & (GL - 1);
     XYZZ<F> *slot = reinterpret_cast<XYZZ<F> *>(smraw) + (threadIdx.x >> 5) * 32;
     const int S = 1 << s, nr = N >> s, nc = S - 1;
     const size_t n_items = (size_t)n_dom * (nr + nc);
-    size_t item = ((((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) << 2) + (lane >> 3);
+    size_t item = ((((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (32 / GL)) + (lane / GL);
     const bool live = item < n_items;
     int dom = 0, idx = 0;
     XYZZ<F> acc = XYZZ<F>::inf();
@@ -342,15 +394,15 @@ __global__ void __launch_bounds__(RED_T) k_rowcol_sums(const XYZZ<F> *__restrict
         const XYZZ<F> *p = B + (size_t)dom * N;
         if (idx < nr) {
             int hi = idx + 1;
-            for (int lo = sub; lo < S; lo += 8) { int d = hi * S + lo; if (d <= N) acc.add(p[d - 1]); }
+            for (int lo = sub; lo < S; lo += GL) { int d = hi * S + lo; if (d <= N) acc.add(p[d - 1]); }
         } else {
             int lo = idx - nr + 1;
-            for (int hi = sub; hi <= nr; hi += 8) { int d = hi * S + lo; if (d <= N) acc.add(p[d - 1]); }
+            for (int hi = sub; hi <= nr; hi += GL) { int d = hi * S + lo; if (d <= N) acc.add(p[d - 1]); }
         }
     }
     slot[lane] = acc;
     __syncwarp();
-    for (int o = 4; o > 0; o >>= 1) {
+    for (int o = GL / 2; o > 0; o >>= 1) {
         if (sub < (uint32_t)o) { XYZZ<F> x = slot[lane]; x.add(slot[lane + o]); slot[lane] = x; }
         __syncwarp();
     }

@@ -35,8 +35,8 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
     t_max += NB + 1;
     const size_t pt = sizeof(XYZZ<F>);
     ZK_TRY(ctx->digits.reserve(E * 4));
-    ZK_TRY(ctx->tile_hist.reserve(n_dom * tiles * (size_t)nbins * 4));
-    ZK_TRY(ctx->tile_off.reserve(n_dom * tiles * (size_t)nbins * 4));
+    ZK_TRY(ctx->tile_hist.reserve(n_dom * tiles * (size_t)(c > 16 ? 512 : nbins) * 4));
+    ZK_TRY(ctx->tile_off.reserve(n_dom * tiles * (size_t)(c > 16 ? 512 : nbins) * 4));
     ZK_TRY(ctx->sizes.reserve((NB + 1) * 4));
     ZK_TRY(ctx->bucket_off.reserve((NB + 1) * 4));
     ZK_TRY(ctx->task_off.reserve((NB + 1) * 4));
@@ -55,19 +55,36 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
         dim3 g((unsigned)((n + 255) / 256), (unsigned)batch);
         k_msm_digits<<<g, 256, 0, st>>>(d_scalars, (uint32_t)n, c, W, digits, ctx->d_err);
     }
-    // 2. counting sort per domain
-    size_t smem = (size_t)nbins * 4;
+    // 2. counting sort per domain.  Up to 16-bit windows the 2^(c-1) bucket counters fit in shared memory (one level);
+    //    wider windows sort by the high 9 key bits first and finish each coarse bin in shared memory (k_fine_sort).
+    const bool two_level = c > 16;
+    const int low = two_level ? (c - 1) - 9 : 0, sort_bins = two_level ? 512 : nbins;
+    const size_t SB = n_dom * (size_t)sort_bins;
+    size_t smem = (size_t)sort_bins * 4;
     if (smem > 48 * 1024) {
         ZK_CUDA(cudaFuncSetAttribute(k_tile_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ZK_CUDA(cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     dim3 gs((unsigned)tiles, (unsigned)n_dom);
-    k_tile_hist<<<gs, SORT_THREADS, smem, st>>>(digits, e_dom, nbins, ctx->tile_hist.as<uint32_t>(), tiles);
-    k_col_scan<<<(unsigned)((NB + 255) / 256), 256, 0, st>>>(ctx->tile_hist.as<uint32_t>(), ctx->tile_off.as<uint32_t>(), ctx->sizes.as<uint32_t>(),
-                                                            nbins, tiles, (int)n_dom);
-    exclusive_scan<false>(ctx->sizes.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(), NB, ctx->scan_scratch.as<uint32_t>(), st);
-    k_scatter<<<gs, SORT_THREADS, smem, st>>>(digits, e_dom, nbins, ctx->tile_off.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(),
-                                              ctx->sorted.as<uint32_t>(), tiles);
+    if (!two_level) {
+        k_tile_hist<<<gs, SORT_THREADS, smem, st>>>(digits, e_dom, nbins, 0, ctx->tile_hist.as<uint32_t>(), tiles);
+        k_col_scan<<<(unsigned)((NB + 255) / 256), 256, 0, st>>>(ctx->tile_hist.as<uint32_t>(), ctx->tile_off.as<uint32_t>(), ctx->sizes.as<uint32_t>(),
+                                                                nbins, tiles, (int)n_dom);
+        exclusive_scan<false>(ctx->sizes.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(), NB, ctx->scan_scratch.as<uint32_t>(), st);
+        k_scatter<<<gs, SORT_THREADS, smem, st>>>(digits, e_dom, nbins, 0, ctx->tile_off.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(),
+                                                  ctx->sorted.as<uint32_t>(), tiles);
+    } else {
+        ZK_TRY(ctx->sorted2.reserve(E * 4));
+        ZK_TRY(ctx->coarse_off.reserve((SB + 1) * 4)); ZK_TRY(ctx->coarse_sizes.reserve((SB + 1) * 4));
+        k_tile_hist<<<gs, SORT_THREADS, smem, st>>>(digits, e_dom, sort_bins, low, ctx->tile_hist.as<uint32_t>(), tiles);
+        k_col_scan<<<(unsigned)((SB + 255) / 256), 256, 0, st>>>(ctx->tile_hist.as<uint32_t>(), ctx->tile_off.as<uint32_t>(), ctx->coarse_sizes.as<uint32_t>(),
+                                                                sort_bins, tiles, (int)n_dom);
+        exclusive_scan<false>(ctx->coarse_sizes.as<uint32_t>(), ctx->coarse_off.as<uint32_t>(), SB, ctx->scan_scratch.as<uint32_t>(), st);
+        k_scatter<<<gs, SORT_THREADS, smem, st>>>(digits, e_dom, sort_bins, low, ctx->tile_off.as<uint32_t>(), ctx->coarse_off.as<uint32_t>(),
+                                                  ctx->sorted2.as<uint32_t>(), tiles);
+        k_fine_sort<<<dim3(512, (unsigned)n_dom), 1024, 0, st>>>(ctx->sorted2.as<uint32_t>(), ctx->coarse_off.as<uint32_t>(), digits, e_dom, 512, low,
+                                                                 ctx->sizes.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(), ctx->sorted.as<uint32_t>());
+    }
     // 2b. batched-affine pre-reduction (msm_affine.cuh): each level halves every bucket at ~6.4 products per addition
     //     instead of the 10 of an XYZZ mixed addition.  MEASURED (round 1, 2^20 terms): 9.1 ms (1 level) / 9.3 ms (2 levels)
     //     against 8.3 ms without — the per-thread binary-Euclid inversion diverges inside a warp and the two passes over
@@ -137,16 +154,20 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
         k_sum_points<F><<<(unsigned)((n_g * 32 + RED_T - 1) / RED_T), RED_T, sm_warp, st>>>(part, slices, (int)n_g, X);
         k_finish_bits<F><<<(unsigned)((n_dom * 32 + RED_T - 1) / RED_T), RED_T, sm_warp, st>>>(X, bits, (int)n_dom, out);
     };
-    if (tables && n_dom >= 8 && c >= 7) {
+    if (tables && ((n_dom >= 8 && c >= 7) || c > 16)) {
         // many domains (batched proving): two-level row/column scheme, 2 additions per bucket (msm.cuh)
         const int s = (c - 1) / 2, nr = nbins >> s, nc = (1 << s) - 1;
         ZK_TRY(ctx->red_rows.reserve(n_dom * (size_t)(nr + nc + 2) * pt));
-        if (sm_warp > 48 * 1024) ZK_CUDA(cudaFuncSetAttribute(k_rowcol_sums<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_warp));
+        if (sm_warp > 48 * 1024) {
+            ZK_CUDA(cudaFuncSetAttribute(k_rowcol_sums<F, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_warp));
+            ZK_CUDA(cudaFuncSetAttribute(k_rowcol_sums<F, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_warp));
+        }
         XYZZ<F> *rows = ctx->red_rows.as<XYZZ<F>>(), *cols = rows + n_dom * (size_t)nr, *Rr = R + n_dom + 1, *Rc = cols + n_dom * (size_t)nc;
         ZK_TRY(ctx->result.reserve((2 * n_dom + batch + 2) * pt));
         R = ctx->result.as<XYZZ<F>>(); Rr = R + n_dom + 1;
         size_t n_w = n_dom * (size_t)(nr + nc);
-        k_rowcol_sums<F><<<(unsigned)((((n_w + 3) / 4) * 32 + RED_T - 1) / RED_T), RED_T, sm_warp, st>>>(buckets, nbins, s, (int)n_dom, rows, cols);
+        if (n_dom >= 8) k_rowcol_sums<F, 8><<<(unsigned)((((n_w + 3) / 4) * 32 + RED_T - 1) / RED_T), RED_T, sm_warp, st>>>(buckets, nbins, s, (int)n_dom, rows, cols);
+        else k_rowcol_sums<F, 32><<<(unsigned)((n_w * 32 + RED_T - 1) / RED_T), RED_T, sm_warp, st>>>(buckets, nbins, s, (int)n_dom, rows, cols);
         bit_reduce(rows, nr, c - s, Rr);            // hi in [1, 2^(c-1-s)]: c-s bits
         bit_reduce(cols, nc, s, Rc);                // lo in [1, 2^s - 1]: s bits
         k_join_rowcol<F><<<(unsigned)((n_dom + 63) / 64), 64, 0, st>>>(Rr, Rc, s, (int)n_dom, R);
