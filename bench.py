@@ -35,7 +35,8 @@ N_SETS = 8                     # distinct scalar vectors cycled through: 8 x 32 
 KERNELS_PER_MSM = 18           # digits, tile_hist, col_scan, 2 x (scan_block, scan_block, scan_add), scatter, pick_task_len,
                                # accumulate, combine_serial, combine_warp, bit_sums, sum_points, finish_bits, encode
                                # (counted from the ncu launch list profiles/r01_launches_msm_2p20.csv; N > 1 adds the fold kernel)
-ALGO_MODMUL_PER_TERM = 176     # 11 (mixed add) x ceil(255/16) windows — SURVEY.md §8(d) / BASELINE.md §3
+ALGO_MODMUL_PER_TERM = 176     # 11 (mixed add) x ceil(255/16) windows — the FIXED convention of SURVEY.md §8(d) / BASELINE.md §3,
+                               # independent of the window size the library actually uses
 ALGO_BYTES_PER_TERM = 128      # 96 B base + 32 B scalar
 
 
@@ -263,7 +264,7 @@ def run_ours(args):
             "config": {"workload": "G1 Pippenger MSM, 2^%d uniform-random subgroup bases per GPU (bases sharded by index range, "
                                    "partial sums all-gathered over NCCL), uniform Fr scalars" % args.log_n,
                        "window_bits": bases.window_bits, "precomputed_window_tables": True,
-                       "l2_policy": "inputs larger than L2: %d distinct 32 MiB scalar vectors cycled, 1.5 GiB window tables gathered randomly" % N_SETS,
+                       "l2_policy": "inputs larger than L2: %d distinct 32 MiB scalar vectors cycled, %.2f GiB window tables gathered randomly" % (N_SETS, (255 // bases.window_bits + 1) * n * 96 / 2**30),
                        "setup_s_untimed": round(setup_s, 2)},
             "e2e": {"value": e2e_value, "unit": "Mop/s", "h2d_bytes_per_step": n * 32 * world, "d2h_bytes_per_step": 96 * world,
                     "ms_per_step": ms_e2e / args.steps, "api": "zk_msm (C ABI, scalars in pinned host memory)"},
@@ -434,7 +435,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log-n", dest="log_n", type=int, default=LOG_N)
-    ap.add_argument("--window-bits", dest="window_bits", type=int, default=16)
+    ap.add_argument("--window-bits", dest="window_bits", type=int, default=0, help="0 = library default (20 bits from 2^20 terms, else <= 16)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-secondary", dest="secondary", action="store_false")
     args = ap.parse_args()

@@ -48,7 +48,7 @@ extern "C" void zk_ctx_destroy(zk_ctx *c) {
     DevBuf *bufs[] = {&c->scalars, &c->digits, &c->tile_hist, &c->tile_off, &c->sizes, &c->bucket_off, &c->task_off, &c->scan_scratch,
                       &c->sorted, &c->partials, &c->buckets, &c->red_part, &c->red_x, &c->result, &c->out_bytes, &c->stage_a, &c->stage_b,
                       &c->stage_c, &c->ntt_tw, &c->ntt_tmp, &c->g_a, &c->g_b, &c->g_c, &c->g_h, &c->g_scal, &c->g_misc,
-                      &c->aff_pts0, &c->aff_pts1, &c->aff_scratch, &c->aff_off0, &c->aff_off1, &c->aff_sizes0, &c->aff_sizes1, &c->red_rows, &c->g_scal2, &c->g_scal3, &c->sorted2, &c->coarse_off, &c->coarse_sizes};
+                      &c->aff_pts0, &c->aff_pts1, &c->aff_scratch, &c->aff_off0, &c->aff_off1, &c->aff_sizes0, &c->aff_sizes1, &c->red_rows, &c->g_scal2, &c->g_scal3, &c->sorted2, &c->coarse_off, &c->coarse_sizes, &c->task_order, &c->len_hist, &c->heavy_list};
     for (DevBuf *b : bufs) b->release();
     if (c->d_err) cudaFree(c->d_err);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -72,9 +72,14 @@ int zk_check_err_flag(zk_ctx *ctx) {
 }
 
 // ---- bases ------------------------------------------------------------------------------------------
-static int pick_window(size_t n) {
+// Window size.  With precomputed tables all windows share one bucket set, so the cost is n * W mixed additions plus a
+// reduction of 2^(c-1) buckets: 16 bits (W = 16, shared-memory one-level sort) up to 2^20 terms, 20 bits (W = 13,
+// two-level sort) from 2^20 terms on — measured 7.7 ms vs 8.1 ms at 2^20.  17..19 bits are never picked: their top
+// window holds only 8 / 3 / 0 scalar bits, which piles n/256 .. n entries into a few buckets.
+static int pick_window(size_t n, bool tables) {
     int lg = 0;
     while (((size_t)1 << (lg + 1)) <= n) lg++;
+    if (tables && lg >= 20) return 20;
     int c = lg - 1;
     if (c < 5) c = 5;
     if (c > 16) c = 16;
@@ -94,7 +99,7 @@ int zk_bases_from_device(zk_ctx *ctx, int group, const void *d_points, size_t n,
     ZK_TRY(zk_use_device(ctx));
     zk_bases *b = new zk_bases();
     b->group = group; b->device = ctx->device; b->n = n;
-    b->c = window_bits > 0 ? window_bits : pick_window(n);
+    b->c = window_bits > 0 ? window_bits : pick_window(n, precompute != 0);
     if (b->c < 2 || b->c > 20 || (b->c > 16 && !precompute)) { delete b; zk_set_error("window_bits must be in [2,16] (17..20 with precomputed tables)"); return ZK_ERR_INVALID; }
     b->W = 255 / b->c + 1;
     b->tables = precompute != 0;

@@ -194,6 +194,7 @@ __device__ __forceinline__ uint32_t scan_load(const uint32_t *in, size_t i, uint
 // accumulation kernel runs in waves of `capacity` (= resident threads) tasks; the length is chosen so that the
 // task count is just under a whole number of waves (a trailing partial wave costs a full wave's latency).
 static __global__ void k_pick_task_len(const uint32_t *__restrict__ total_entries, uint32_t *__restrict__ task_len, uint32_t capacity) {
+    task_len[1] = 0;                                           // heavy-bucket counter of k_combine_serial (next word)
     uint32_t total = *total_entries;
     uint32_t waves = (total + (uint32_t)TASK_LEN_MAX * capacity - 1) / ((uint32_t)TASK_LEN_MAX * capacity);
     if (waves < 2) waves = 2;                                   // small inputs: at least two waves of short tasks
@@ -253,40 +254,92 @@ inline void exclusive_scan(const uint32_t *in, uint32_t *out, size_t n, uint32_t
     cudaMemcpyAsync(out + n, bo + nb, 4, cudaMemcpyDeviceToDevice, st);
 }
 
+// ---- 2c. task order by length -------------------------------------------------------------------------------------
+// Tasks of one warp should run the same number of additions.  With ~equal buckets (one big MSM, 16-bit windows) they do;
+// with short Poisson-distributed buckets (batched proving, wide windows) they do not, and a warp runs as long as its
+// longest task.  Tasks are therefore issued in order of DECREASING length: a counting sort of the tasks by length
+// (<= 255 after clamping), block-aggregated so that global atomics are one per (block, length).
+constexpr int LEN_BINS = 256, LEN_BLOCK = 1024;
+__device__ __forceinline__ uint32_t task_len_of(const uint32_t *bucket_off, const uint32_t *task_off, uint32_t b, uint32_t &nt) {
+    nt = task_off[b + 1] - task_off[b];
+    if (!nt) return 0;
+    uint32_t size = bucket_off[b + 1] - bucket_off[b], len = (size + nt - 1) / nt;
+    return len < (uint32_t)LEN_BINS ? len : (uint32_t)LEN_BINS - 1;
+}
+static __global__ void __launch_bounds__(LEN_BLOCK) k_len_hist(const uint32_t *__restrict__ bucket_off, const uint32_t *__restrict__ task_off,
+                                                              uint32_t n_buckets, uint32_t *__restrict__ ghist) {
+    __shared__ uint32_t sh[LEN_BINS];
+    if (threadIdx.x < LEN_BINS) sh[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t b = blockIdx.x * LEN_BLOCK + threadIdx.x, nt = 0;
+    if (b < n_buckets) { uint32_t len = task_len_of(bucket_off, task_off, b, nt); if (nt) atomicAdd(&sh[len], nt); }
+    __syncthreads();
+    if (threadIdx.x < LEN_BINS && sh[threadIdx.x]) atomicAdd(&ghist[threadIdx.x], sh[threadIdx.x]);
+}
+// one block: cursor[l] = number of tasks longer than l (exclusive scan from the long end); ghist is cleared for the next MSM
+static __global__ void __launch_bounds__(LEN_BINS) k_len_scan(uint32_t *__restrict__ ghist, uint32_t *__restrict__ cursor) {
+    __shared__ uint32_t sh[LEN_BINS];
+    sh[threadIdx.x] = ghist[LEN_BINS - 1 - threadIdx.x];      // reversed: index 0 = longest
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t run = 0; for (int i = 0; i < LEN_BINS; i++) { uint32_t v = sh[i]; sh[i] = run; run += v; } }
+    __syncthreads();
+    cursor[LEN_BINS - 1 - threadIdx.x] = sh[threadIdx.x];
+    ghist[threadIdx.x] = 0;
+}
+static __global__ void __launch_bounds__(LEN_BLOCK) k_len_place(const uint32_t *__restrict__ bucket_off, const uint32_t *__restrict__ task_off,
+                                                               uint32_t n_buckets, uint32_t *__restrict__ cursor, uint32_t *__restrict__ order) {
+    __shared__ uint32_t cnt[LEN_BINS], base[LEN_BINS];
+    if (threadIdx.x < LEN_BINS) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t b = blockIdx.x * LEN_BLOCK + threadIdx.x, nt = 0, len = 0, local = 0;
+    if (b < n_buckets) { len = task_len_of(bucket_off, task_off, b, nt); if (nt) local = atomicAdd(&cnt[len], nt); }
+    __syncthreads();
+    if (threadIdx.x < LEN_BINS && cnt[threadIdx.x]) base[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], cnt[threadIdx.x]);
+    __syncthreads();
+    if (nt) {
+        uint32_t pos = base[len] + local, t0 = task_off[b];
+        for (uint32_t s = 0; s < nt; s++) order[pos + s] = t0 + s;
+    }
+}
+
 // ---- 3. bucket accumulation: k_accumulate lives in msm_accum.cuh (shared with the hot translation unit) ----
 // buckets[b] = sum of the bucket's task partials.  Thread per bucket for the common short case (serial
 // adds; a warp with few live lanes wastes its issue slots), one warp per bucket for heavy (skewed) buckets.
 constexpr uint32_t COMB_SERIAL_MAX = 32;
 template <class F>
 __global__ void __launch_bounds__(128) k_combine_serial(const XYZZ<F> *__restrict__ partials, const uint32_t *__restrict__ task_off,
-                                                        uint32_t n_buckets, XYZZ<F> *__restrict__ buckets) {
+                                                        uint32_t n_buckets, XYZZ<F> *__restrict__ buckets,
+                                                        uint32_t *__restrict__ heavy_list, uint32_t *__restrict__ heavy_count) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_buckets) return;
     uint32_t t0 = task_off[b], t1 = task_off[b + 1];
-    if (t1 - t0 > COMB_SERIAL_MAX) return;
+    if (t1 - t0 > COMB_SERIAL_MAX) { heavy_list[atomicAdd(heavy_count, 1u)] = b; return; }     // rare: left to k_combine_warp
     XYZZ<F> acc = XYZZ<F>::inf();
     if (t1 > t0) acc = partials[t0];
     for (uint32_t t = t0 + 1; t < t1; t++) acc.add(partials[t]);
     buckets[b] = acc;
 }
+// fixed-size grid: warp w folds the heavy buckets heavy_list[w], heavy_list[w + n_warps], ...
 template <class F>
 __global__ void __launch_bounds__(128) k_combine_warp(const XYZZ<F> *__restrict__ partials, const uint32_t *__restrict__ task_off,
-                                                      uint32_t n_buckets, XYZZ<F> *__restrict__ buckets) {
+                                                      const uint32_t *__restrict__ heavy_list, const uint32_t *__restrict__ heavy_count,
+                                                      XYZZ<F> *__restrict__ buckets) {
     extern __shared__ unsigned char smraw[];
     XYZZ<F> *sm = reinterpret_cast<XYZZ<F> *>(smraw) + (threadIdx.x >> 5) * 32;
-    uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (b >= n_buckets) return;
-    uint32_t t0 = task_off[b], t1 = task_off[b + 1];
-    if (t1 - t0 <= COMB_SERIAL_MAX) return;
-    XYZZ<F> acc = XYZZ<F>::inf();
-    for (uint32_t t = t0 + lane; t < t1; t += 32) acc.add(partials[t]);
-    sm[lane] = acc;
-    __syncwarp();
-    for (int o = 16; o > 0; o >>= 1) {
-        if (lane < o) { XYZZ<F> x = sm[lane]; x.add(sm[lane + o]); sm[lane] = x; }
+    const uint32_t lane = threadIdx.x & 31, n_warps = (gridDim.x * blockDim.x) >> 5, n_heavy = *heavy_count;
+    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_heavy; i += n_warps) {
+        uint32_t b = heavy_list[i], t0 = task_off[b], t1 = task_off[b + 1];
+        XYZZ<F> acc = XYZZ<F>::inf();
+        for (uint32_t t = t0 + lane; t < t1; t += 32) acc.add(partials[t]);
         __syncwarp();
+        sm[lane] = acc;
+        __syncwarp();
+        for (int o = 16; o > 0; o >>= 1) {
+            if (lane < (uint32_t)o) { XYZZ<F> x = sm[lane]; x.add(sm[lane + o]); sm[lane] = x; }
+            __syncwarp();
+        }
+        if (lane == 0) buckets[b] = sm[0];
     }
-    if (lane == 0) buckets[b] = sm[0];
 }
 
 // ---- 4. bucket reduction: R = sum_{d=1..N} d * B[d-1] ------------------------------------------------
@@ -376,10 +429,12 @@ __global__ void __launch_bounds__(RED_T) k_finish_bits(const XYZZ<F> *__restrict
 // EIGHT lanes per (domain, row hi = 1..N/S) or (domain, column lo = 1..S-1): each lane adds every 8th element serially,
 // then a 3-level tree inside the group (a full warp per row would spend most of its issue slots in the tree).
 // rows[dom][hi-1], cols[dom][lo-1].
-// GL lanes per item: 8 for many domains (work-bound), 32 for one large domain (depth-bound: long rows).
+// Output rc[(2*dom + which) * NR + idx], NR = N >> s: which = 0 rows (idx = hi-1), which = 1 columns (idx = lo-1, the
+// tail idx >= S-1 stays at the all-zero infinity pattern written by a memset), so ONE per-bit reduction over 2*n_dom
+// pseudo-domains of NR points finishes both weighted sums.
+// GL lanes per item: 8 for many domains (work-bound), 32 inside a warp.
 template <class F, int GL>
-__global__ void __launch_bounds__(RED_T) k_rowcol_sums(const XYZZ<F> *__restrict__ B, int N, int s, int n_dom,
-                                                       XYZZ<F> *__restrict__ rows, XYZZ<F> *__restrict__ cols) {
+__global__ void __launch_bounds__(RED_T) k_rowcol_sums(const XYZZ<F> *__restrict__ B, int N, int s, int n_dom, XYZZ<F> *__restrict__ rc) {
     extern __shared__ unsigned char smraw[];
     const uint32_t lane = threadIdx.x & 31, sub = lane & (GL - 1);
     XYZZ<F> *slot = reinterpret_cast<XYZZ<F> *>(smraw) + (threadIdx.x >> 5) * 32;
@@ -406,16 +461,45 @@ __global__ void __launch_bounds__(RED_T) k_rowcol_sums(const XYZZ<F> *__restrict
         if (sub < (uint32_t)o) { XYZZ<F> x = slot[lane]; x.add(slot[lane + o]); slot[lane] = x; }
         __syncwarp();
     }
-    if (live && sub == 0) { if (idx < nr) rows[(size_t)dom * nr + idx] = slot[lane]; else cols[(size_t)dom * nc + (idx - nr)] = slot[lane]; }
+    if (live && sub == 0) {
+        if (idx < nr) rc[((size_t)2 * dom) * nr + idx] = slot[lane]; else rc[((size_t)2 * dom + 1) * nr + (idx - nr)] = slot[lane];
+    }
 }
-// thread per domain: R = 2^s * Rrows + Rcols
+// one BLOCK (RED_T threads) per item: a single large domain has long rows / columns and few items.  (Cutting the
+// rows into chunks with a warp each was measured slower: the warp-level trees dominate the issue slots.)
 template <class F>
-__global__ void k_join_rowcol(const XYZZ<F> *__restrict__ Rrows, const XYZZ<F> *__restrict__ Rcols, int s, int n_dom, XYZZ<F> *__restrict__ R) {
+__global__ void __launch_bounds__(RED_T) k_rowcol_block(const XYZZ<F> *__restrict__ B, int N, int s, int n_dom, XYZZ<F> *__restrict__ rc) {
+    extern __shared__ unsigned char smraw[];
+    XYZZ<F> *sm = reinterpret_cast<XYZZ<F> *>(smraw);
+    const int S = 1 << s, nr = N >> s, nc = S - 1;
+    const int dom = blockIdx.x / (nr + nc), idx = blockIdx.x % (nr + nc);
+    const XYZZ<F> *p = B + (size_t)dom * N;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    if (idx < nr) {
+        int hi = idx + 1;
+        for (int lo = threadIdx.x; lo < S; lo += RED_T) { int d = hi * S + lo; if (d <= N) acc.add(p[d - 1]); }
+    } else {
+        int lo = idx - nr + 1;
+        for (int hi = threadIdx.x; hi <= nr; hi += RED_T) { int d = hi * S + lo; if (d <= N) acc.add(p[d - 1]); }
+    }
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = RED_T >> 1; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) { XYZZ<F> x = sm[threadIdx.x]; x.add(sm[threadIdx.x + o]); sm[threadIdx.x] = x; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (idx < nr) rc[((size_t)2 * dom) * nr + idx] = sm[0]; else rc[((size_t)2 * dom + 1) * nr + (idx - nr)] = sm[0];
+    }
+}
+// thread per domain: R = 2^s * Rrc[2 dom] + Rrc[2 dom + 1]
+template <class F>
+__global__ void k_join_rowcol(const XYZZ<F> *__restrict__ Rrc, int s, int n_dom, XYZZ<F> *__restrict__ R) {
     int dom = blockIdx.x * blockDim.x + threadIdx.x;
     if (dom >= n_dom) return;
-    XYZZ<F> r = Rrows[dom];
+    XYZZ<F> r = Rrc[2 * dom];
     for (int k = 0; k < s; k++) r = r.dbl();
-    r.add(Rcols[dom]);
+    r.add(Rrc[2 * dom + 1]);
     R[dom] = r;
 }
 

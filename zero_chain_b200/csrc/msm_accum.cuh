@@ -25,10 +25,11 @@ __device__ __forceinline__ Affine<F> load_affine(const Affine<F> *__restrict__ p
 template <class F, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_accumulate(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ sorted,
                                                     const uint32_t *__restrict__ bucket_off, const uint32_t *__restrict__ task_off,
-                                                    uint32_t n_buckets, XYZZ<F> *__restrict__ partials) {
+                                                    uint32_t n_buckets, const uint32_t *__restrict__ order, XYZZ<F> *__restrict__ partials) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t n_tasks = task_off[n_buckets];
     if (t >= n_tasks) return;
+    if (order) t = order[t];          // tasks issued by decreasing length (k_len_place): equal work inside a warp
     // bucket of task t: last b with task_off[b] <= t
     uint32_t lo = 0, hi = n_buckets;
     while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (task_off[mid] <= t) lo = mid; else hi = mid; }

@@ -46,8 +46,8 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
     ZK_TRY(ctx->buckets.reserve(NB * pt));
     const int n_bits = c;                      // digit values d in [1, 2^(c-1)] need c bits
     const int n_slices = (nbins / 2 + RED_SLICE / 2 - 1) / (RED_SLICE / 2) > 0 ? (nbins / 2 + RED_SLICE / 2 - 1) / (RED_SLICE / 2) : 1;   // slices of RED_SLICE/2 qualifying digit values
-    ZK_TRY(ctx->red_part.reserve(n_dom * n_bits * (size_t)n_slices * pt));
-    ZK_TRY(ctx->red_x.reserve(n_dom * n_bits * pt));
+    ZK_TRY(ctx->red_part.reserve(2 * n_dom * n_bits * (size_t)n_slices * pt));      // x2: the row/column scheme runs 2 pseudo-domains per domain
+    ZK_TRY(ctx->red_x.reserve(2 * n_dom * n_bits * pt));
     ZK_TRY(ctx->result.reserve((n_dom + batch + 1) * pt));
 
     uint32_t *digits = ctx->digits.as<uint32_t>();
@@ -123,6 +123,24 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
     // 3. accumulate + combine.  The payload of an entry is its position in the domain = [w][i] index;
     //    with tables that is the table index when n == b->n (checked by the callers).
     XYZZ<F> *partials = ctx->partials.as<XYZZ<F>>(), *buckets = ctx->buckets.as<XYZZ<F>>();
+    // task order by decreasing length when buckets are short and uneven (batched proving, wide windows); one large MSM with
+    // 16-bit windows has ~equal tasks already and skips it
+    const uint32_t *order = nullptr;
+    {
+        static int ord_env = -2;
+        if (ord_env == -2) { const char *e = getenv("ZK_TASK_ORDER"); ord_env = e ? atoi(e) : -1; }
+        bool want = ord_env >= 0 ? ord_env != 0 : (E / NB < 256);
+        if (want) {
+            ZK_TRY(ctx->task_order.reserve(t_max * 4)); ZK_TRY(ctx->len_hist.reserve(2 * LEN_BINS * 4 + 64));
+            uint32_t *gh = ctx->len_hist.as<uint32_t>(), *cur = gh + LEN_BINS;
+            if (!ctx->len_hist_zeroed) { ZK_CUDA(cudaMemsetAsync(gh, 0, 2 * LEN_BINS * 4, st)); ctx->len_hist_zeroed = true; }
+            unsigned nb = (unsigned)((NB + LEN_BLOCK - 1) / LEN_BLOCK);
+            k_len_hist<<<nb, LEN_BLOCK, 0, st>>>(cur_off, ctx->task_off.as<uint32_t>(), (uint32_t)NB, gh);
+            k_len_scan<<<1, LEN_BINS, 0, st>>>(gh, cur);
+            k_len_place<<<nb, LEN_BLOCK, 0, st>>>(cur_off, ctx->task_off.as<uint32_t>(), (uint32_t)NB, cur, ctx->task_order.as<uint32_t>());
+            order = ctx->task_order.as<uint32_t>();
+        }
+    }
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (ctx->prof_on) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, st); }
     {
@@ -131,9 +149,9 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
         const Affine<F> *tb = cur_pts;
         const uint32_t *so = cur_sorted, *bo = cur_off, *to = ctx->task_off.as<uint32_t>();
         unsigned grid = (unsigned)((t_max + 127) / 128);
-        if (minb == 3) k_accumulate<F, 3><<<grid, 128, 0, st>>>(tb, so, bo, to, (uint32_t)NB, partials);
-        else if (minb == 4) k_accumulate<F, 4><<<grid, 128, 0, st>>>(tb, so, bo, to, (uint32_t)NB, partials);
-        else k_accumulate<F, 2><<<grid, 128, 0, st>>>(tb, so, bo, to, (uint32_t)NB, partials);
+        if (minb == 3) k_accumulate<F, 3><<<grid, 128, 0, st>>>(tb, so, bo, to, (uint32_t)NB, order, partials);
+        else if (minb == 4) k_accumulate<F, 4><<<grid, 128, 0, st>>>(tb, so, bo, to, (uint32_t)NB, order, partials);
+        else k_accumulate<F, 2><<<grid, 128, 0, st>>>(tb, so, bo, to, (uint32_t)NB, order, partials);
     }
     if (ctx->prof_on) { cudaEventRecord(ev1, st); ctx->prof_events.push_back(ev0); ctx->prof_events.push_back(ev1); }
     const size_t sm_warp = 4 * 32 * pt;      // 4 warps x 32 points
@@ -143,38 +161,41 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
         ZK_CUDA(cudaFuncSetAttribute(k_sum_points<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_warp));
         ZK_CUDA(cudaFuncSetAttribute(k_finish_bits<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_warp));
     }
-    k_combine_serial<F><<<(unsigned)((NB + 127) / 128), 128, 0, st>>>(partials, ctx->task_off.as<uint32_t>(), (uint32_t)NB, buckets);
-    k_combine_warp<F><<<(unsigned)((NB * 32 + 127) / 128), 128, sm_warp, st>>>(partials, ctx->task_off.as<uint32_t>(), (uint32_t)NB, buckets);
+    ZK_TRY(ctx->heavy_list.reserve((NB + 1) * 4));
+    uint32_t *heavy_count = d_task_len + 1;       // cleared by k_pick_task_len
+    k_combine_serial<F><<<(unsigned)((NB + 127) / 128), 128, 0, st>>>(partials, ctx->task_off.as<uint32_t>(), (uint32_t)NB, buckets,
+                                                                      ctx->heavy_list.as<uint32_t>(), heavy_count);
+    k_combine_warp<F><<<(unsigned)(2 * ctx->sm_count), 128, sm_warp, st>>>(partials, ctx->task_off.as<uint32_t>(), ctx->heavy_list.as<uint32_t>(), heavy_count, buckets);
     // 4. bucket reduction per domain
     XYZZ<F> *part = ctx->red_part.as<XYZZ<F>>(), *X = ctx->red_x.as<XYZZ<F>>(), *R = ctx->result.as<XYZZ<F>>();
-    auto bit_reduce = [&](const XYZZ<F> *Bk, int N, int bits, XYZZ<F> *out) {     // out[dom] = sum_{d=1..N} d * Bk[dom][d-1]
+    auto bit_reduce = [&](const XYZZ<F> *Bk, int N, int bits, size_t nd, XYZZ<F> *out) {     // out[dom] = sum_{d=1..N} d * Bk[dom][d-1]
         int slices = (N / 2 + RED_SLICE / 2 - 1) / (RED_SLICE / 2); if (slices < 1) slices = 1;
-        size_t n_w = (size_t)slices * bits * n_dom, n_g = n_dom * (size_t)bits;
-        k_bit_sums<F><<<(unsigned)((n_w * 32 + RED_T - 1) / RED_T), RED_T, sm_warp, st>>>(Bk, N, slices, bits, (int)n_dom, part);
+        size_t n_w = (size_t)slices * bits * nd, n_g = nd * (size_t)bits;
+        k_bit_sums<F><<<(unsigned)((n_w * 32 + RED_T - 1) / RED_T), RED_T, sm_warp, st>>>(Bk, N, slices, bits, (int)nd, part);
         k_sum_points<F><<<(unsigned)((n_g * 32 + RED_T - 1) / RED_T), RED_T, sm_warp, st>>>(part, slices, (int)n_g, X);
-        k_finish_bits<F><<<(unsigned)((n_dom * 32 + RED_T - 1) / RED_T), RED_T, sm_warp, st>>>(X, bits, (int)n_dom, out);
+        k_finish_bits<F><<<(unsigned)((nd * 32 + RED_T - 1) / RED_T), RED_T, sm_warp, st>>>(X, bits, (int)nd, out);
     };
     if (tables && ((n_dom >= 8 && c >= 7) || c > 16)) {
-        // many domains (batched proving): two-level row/column scheme, 2 additions per bucket (msm.cuh)
+        // two-level row/column scheme, 2 additions per bucket (msm.cuh): many domains (batched proving) or wide windows
         const int s = (c - 1) / 2, nr = nbins >> s, nc = (1 << s) - 1;
-        ZK_TRY(ctx->red_rows.reserve(n_dom * (size_t)(nr + nc + 2) * pt));
+        ZK_TRY(ctx->red_rows.reserve(2 * n_dom * (size_t)nr * pt));
+        ZK_TRY(ctx->result.reserve((3 * n_dom + batch + 2) * pt));
+        R = ctx->result.as<XYZZ<F>>();
+        XYZZ<F> *rc = ctx->red_rows.as<XYZZ<F>>(), *Rrc = R + n_dom + 1;
         if (sm_warp > 48 * 1024) {
             ZK_CUDA(cudaFuncSetAttribute(k_rowcol_sums<F, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_warp));
-            ZK_CUDA(cudaFuncSetAttribute(k_rowcol_sums<F, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_warp));
+            ZK_CUDA(cudaFuncSetAttribute(k_rowcol_block<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_warp));
         }
-        XYZZ<F> *rows = ctx->red_rows.as<XYZZ<F>>(), *cols = rows + n_dom * (size_t)nr, *Rr = R + n_dom + 1, *Rc = cols + n_dom * (size_t)nc;
-        ZK_TRY(ctx->result.reserve((2 * n_dom + batch + 2) * pt));
-        R = ctx->result.as<XYZZ<F>>(); Rr = R + n_dom + 1;
-        size_t n_w = n_dom * (size_t)(nr + nc);
-        if (n_dom >= 8) k_rowcol_sums<F, 8><<<(unsigned)((((n_w + 3) / 4) * 32 + RED_T - 1) / RED_T), RED_T, sm_warp, st>>>(buckets, nbins, s, (int)n_dom, rows, cols);
-        else k_rowcol_sums<F, 32><<<(unsigned)((n_w * 32 + RED_T - 1) / RED_T), RED_T, sm_warp, st>>>(buckets, nbins, s, (int)n_dom, rows, cols);
-        bit_reduce(rows, nr, c - s, Rr);            // hi in [1, 2^(c-1-s)]: c-s bits
-        bit_reduce(cols, nc, s, Rc);                // lo in [1, 2^s - 1]: s bits
-        k_join_rowcol<F><<<(unsigned)((n_dom + 63) / 64), 64, 0, st>>>(Rr, Rc, s, (int)n_dom, R);
+        size_t n_items = n_dom * (size_t)(nr + nc);
+        ZK_CUDA(cudaMemsetAsync(rc, 0, 2 * n_dom * (size_t)nr * pt, st));          // infinity padding of the column halves
+        if (n_dom >= 8) k_rowcol_sums<F, 8><<<(unsigned)((((n_items + 3) / 4) * 32 + RED_T - 1) / RED_T), RED_T, sm_warp, st>>>(buckets, nbins, s, (int)n_dom, rc);
+        else k_rowcol_block<F><<<(unsigned)n_items, RED_T, sm_warp, st>>>(buckets, nbins, s, (int)n_dom, rc);
+        bit_reduce(rc, nr, c - s, 2 * n_dom, Rrc);      // rows: hi in [1, 2^(c-1-s)] (c-s bits); columns: lo in [1, 2^s - 1]
+        k_join_rowcol<F><<<(unsigned)((n_dom + 63) / 64), 64, 0, st>>>(Rrc, s, (int)n_dom, R);
     } else if (tables) {
-        bit_reduce(buckets, nbins, n_bits, R);
+        bit_reduce(buckets, nbins, n_bits, n_dom, R);
     } else {
-        bit_reduce(buckets, nbins, n_bits, R + 1);
+        bit_reduce(buckets, nbins, n_bits, n_dom, R + 1);
         k_horner_windows<F><<<1, 32, 0, st>>>(R + 1, W, c, R);
     }
     ZK_CUDA(cudaGetLastError());
