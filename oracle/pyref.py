@@ -582,3 +582,184 @@ def groth16_verify(vk, proof_abc, public_inputs) -> bool:
     m = _f12_mul(m, miller_loop(ec_neg(FQ, acc), vk["gamma_g2"]))
     m = _f12_mul(m, miller_loop(ec_neg(FQ, c), vk["delta_g2"]))
     return final_exponentiation(m) == F12_ONE
+
+
+# ---------------------------------------------------------------------------------------
+# PreparedVerifyingKey (core/bellman-verifier/src/lib.rs:110-245) and the strict Proof::read (lib.rs:67-108).
+# The prepared form of a G2 point is the list of line coefficients its Miller loop consumes
+# (G2Prepared::from_affine, core/pairing/src/bls12_381/mod.rs:163-359).  Restated from the curve equations: with
+# T = (X, Y, Z) Jacobian on E'(Fq2),
+#   doubling  (EFD dbl-2009-l):  X3 = 9X^4 - 8XY^2, Z3 = 2YZ, Y3 = 3X^2 (4XY^2 - X3) - 8Y^4
+#             line = (2 Z3 Z^2, -6 X^2 Z^2, 6 X^3 - 4 Y^2)
+#   addition of the affine base point (x2, y2) (EFD madd-2007-bl):  H = x2 Z^2 - X, r = 2 (y2 Z^3 - Y), Z3 = 2ZH,
+#             X3 = r^2 - 4H^3 - 8XH^2, Y3 = r (4XH^2 - X3) - 8YH^3;  line = (2 Z3, -2 r, 2 (r x2 - y2 Z3))
+# Pinned bit-for-bit by the shipped conf_vk.dat / anony_vk.dat (tests/test_oracle_pairing.py): the file's two coefficient
+# tables are prepare(-gamma_g2) and prepare(-delta_g2) of the VerifyingKey inside conf_pk.dat / anony_pk.dat.
+def g2_prepare(q):
+    F = FQ2
+    if q is INF:
+        return []
+    def k(a, n): return ((a[0] * n) % Q, (a[1] * n) % Q)
+    sq = lambda a: F.mul(a, a)
+    X, Y, Z = q[0], q[1], F.one
+    x2, y2 = q
+    out = []
+
+    def dbl():
+        nonlocal X, Y, Z
+        xx, yy, zz = sq(X), sq(Y), sq(Z)
+        xyy4 = k(F.mul(X, yy), 4)
+        e = k(xx, 3)
+        X3 = F.sub(sq(e), k(xyy4, 2))
+        Z3 = k(F.mul(Y, Z), 2)
+        Y3 = F.sub(F.mul(e, F.sub(xyy4, X3)), k(sq(yy), 8))
+        line = (k(F.mul(Z3, zz), 2), F.neg(k(F.mul(e, zz), 2)), F.sub(k(F.mul(e, X), 2), k(yy, 4)))
+        X, Y, Z = X3, Y3, Z3
+        out.append(line)
+
+    def add():
+        nonlocal X, Y, Z
+        zz = sq(Z)
+        h = F.sub(F.mul(x2, zz), X)
+        r = k(F.sub(F.mul(y2, F.mul(Z, zz)), Y), 2)
+        hh = sq(h)
+        Z3 = k(F.mul(Z, h), 2)
+        v4 = k(F.mul(X, hh), 4)
+        h34 = k(F.mul(h, hh), 4)
+        X3 = F.sub(F.sub(sq(r), h34), k(v4, 2))
+        Y3 = F.sub(F.mul(r, F.sub(v4, X3)), k(F.mul(Y, h34), 2))
+        line = (k(Z3, 2), F.neg(k(r, 2)), k(F.sub(F.mul(r, x2), F.mul(y2, Z3)), 2))
+        X, Y, Z = X3, Y3, Z3
+        out.append(line)
+
+    bits = bin(BLS_X)[3:]             # below the leading one; the last bit's doubling closes the list (mod.rs:338-352)
+    for b in bits[:-1]:
+        dbl()
+        if b == "1":
+            add()
+    dbl()
+    assert bits[-1] == "0"
+    return out
+
+
+def _fq2_bytes(a) -> bytes:            # Fq2::write: c0 then c1 (fq2.rs:40-44)
+    return a[0].to_bytes(48, "big") + a[1].to_bytes(48, "big")
+
+
+def g2_prepared_write(coeffs, infinity=False) -> bytes:
+    """G2Prepared::write (core/pairing/src/bls12_381/ec.rs:1631-1650)."""
+    out = bytearray(len(coeffs).to_bytes(4, "big"))
+    for c in coeffs:
+        out += _fq2_bytes(c[0]) + _fq2_bytes(c[1]) + _fq2_bytes(c[2])
+    out += b"\x01" if infinity else b"\x00"
+    return bytes(out)
+
+
+def pvk_write(vk) -> bytes:
+    """prepare_verifying_key (verifier.rs:15-30) followed by PreparedVerifyingKey::write (lib.rs:183-202)."""
+    out = bytearray(f12_to_tower_bytes(pairing_reference(vk["alpha_g1"], vk["beta_g2"])))
+    for g in (vk["gamma_g2"], vk["delta_g2"]):
+        out += g2_prepared_write(g2_prepare(ec_neg(FQ2, g)))
+    out += len(vk["ic"]).to_bytes(4, "big")
+    for p in vk["ic"]:
+        out += g1_uncompressed(p)
+    return bytes(out)
+
+
+def vk_read(buf: bytes) -> dict:
+    """VerifyingKey::read — the head of Parameters::write (alpha_g1, beta_g1, beta_g2, gamma_g2, delta_g1, delta_g2, ic)."""
+    o = 0
+    def g1():
+        nonlocal o
+        p = g1_from_uncompressed(buf[o:o + 96]); o += 96; return p
+    def g2():
+        nonlocal o
+        p = g2_from_uncompressed(buf[o:o + 192]); o += 192; return p
+    vk = dict(alpha_g1=g1(), beta_g1=g1(), beta_g2=g2(), gamma_g2=g2(), delta_g1=g1(), delta_g2=g2())
+    n = int.from_bytes(buf[o:o + 4], "big"); o += 4
+    vk["ic"] = [g1() for _ in range(n)]
+    vk["_size"] = o
+    return vk
+
+
+def vk_write(vk) -> bytes:
+    out = g1_uncompressed(vk["alpha_g1"]) + g1_uncompressed(vk["beta_g1"]) + g2_uncompressed(vk["beta_g2"])
+    out += g2_uncompressed(vk["gamma_g2"]) + g1_uncompressed(vk["delta_g1"]) + g2_uncompressed(vk["delta_g2"])
+    out += len(vk["ic"]).to_bytes(4, "big")
+    return out + b"".join(g1_uncompressed(p) for p in vk["ic"])
+
+
+def _compressed_strict(b: bytes, g2: bool):
+    """Compressed::into_affine (ec.rs:796-838 + subgroup check ec.rs:775-794): raises ValueError like GroupDecodingError."""
+    if not b[0] & 0x80:
+        raise ValueError("UnexpectedCompressionMode")
+    if b[0] & 0x40:
+        if (b[0] & 0x3F) or any(b[1:]):
+            raise ValueError("UnexpectedInformation")
+        return INF
+    F = FQ2 if g2 else FQ
+    if g2:
+        x1 = int.from_bytes(bytes([b[0] & 0x1F]) + b[1:48], "big")
+        x0 = int.from_bytes(b[48:], "big")
+        if x0 >= Q or x1 >= Q:
+            raise ValueError("CoordinateDecodingError")
+    else:
+        if int.from_bytes(bytes([b[0] & 0x1F]) + b[1:], "big") >= Q:
+            raise ValueError("CoordinateDecodingError")
+    p = g2_from_compressed(b) if g2 else g1_from_compressed(b)
+    if ec_mul(F, p, R) is not INF:
+        raise ValueError("NotInSubgroup")
+    return p
+
+
+def proof_read(b: bytes):
+    """Proof::read (lib.rs:67-108): returns (a, b, c); raises ValueError('InvalidData') / ValueError('PointInfinity')."""
+    assert len(b) == 192
+    pts = []
+    for chunk, g2 in ((b[:48], False), (b[48:144], True), (b[144:], False)):
+        try:
+            p = _compressed_strict(chunk, g2)
+        except ValueError:
+            raise ValueError("InvalidData")
+        if p is INF:
+            raise ValueError("PointInfinity")
+        pts.append(p)
+    return tuple(pts)
+
+
+def miller_loop_prepared(p, coeffs):
+    """Engine::miller_loop for one (G1Affine, G2Prepared) pair (mod.rs:40-102): ell() places coeffs.2 at 1, coeffs.1 * x_P at
+    v and coeffs.0 * y_P at v w (mul_by_014), i.e. at w^0, w^2 and w^3 of the polynomial basis used here."""
+    if p is INF or not coeffs:
+        return F12_ONE
+    def ell(c):
+        r = [0] * 12
+        for pos, val in ((0, c[2]), (2, (c[1][0] * p[0] % Q, c[1][1] * p[0] % Q)), (3, (c[0][0] * p[1] % Q, c[0][1] * p[1] % Q))):
+            r[pos] = (r[pos] + val[0] - val[1]) % Q
+            r[pos + 6] = (r[pos + 6] + val[1]) % Q
+        return r
+    it = iter(coeffs)
+    f = F12_ONE
+    bits = bin(BLS_X)[3:]
+    for b in bits[:-1]:
+        f = _f12_mul(f, ell(next(it)))
+        if b == "1":
+            f = _f12_mul(f, ell(next(it)))
+        f = _f12_mul(f, f)
+    f = _f12_mul(f, ell(next(it)))
+    # conjugation = the q^6 Frobenius: w -> -w
+    return [x if i % 2 == 0 else (-x) % Q for i, x in enumerate(f)]
+
+
+def verify_prepared(pvk_alpha_beta, neg_gamma_coeffs, neg_delta_coeffs, ic, proof_abc, public_inputs):
+    """verify_proof (verifier.rs:32-63) on prepared data; returns bool, raises ValueError('MalformedVerifyingKey')."""
+    if len(public_inputs) + 1 != len(ic):
+        raise ValueError("MalformedVerifyingKey")
+    a, b, c = proof_abc
+    acc = ic[0]
+    for x, pt in zip(public_inputs, ic[1:]):
+        acc = ec_add(FQ, acc, ec_mul(FQ, pt, x))
+    m = miller_loop_prepared(a, g2_prepare(b))
+    m = _f12_mul(m, miller_loop_prepared(acc, neg_gamma_coeffs))
+    m = _f12_mul(m, miller_loop_prepared(c, neg_delta_coeffs))
+    return _f12_pow(final_exponentiation(m), 3) == pvk_alpha_beta

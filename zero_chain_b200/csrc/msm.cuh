@@ -465,32 +465,46 @@ __global__ void __launch_bounds__(RED_T) k_rowcol_sums(const XYZZ<F> *__restrict
         if (idx < nr) rc[((size_t)2 * dom) * nr + idx] = slot[lane]; else rc[((size_t)2 * dom + 1) * nr + (idx - nr)] = slot[lane];
     }
 }
-// one BLOCK (RED_T threads) per item: a single large domain has long rows / columns and few items.  (Cutting the
-// rows into chunks with a warp each was measured slower: the warp-level trees dominate the issue slots.)
+// A single large domain has few, long rows / columns.  Trees waste issue slots (a warp-level add costs a full warp even with
+// one live lane), so the sums are done as three stages of purely SERIAL per-thread sums over short runs:
+//   stage 1  thread (slot, k): elements [k*L1, (k+1)*L1) of the slot's row / column        -> t1[slot][k],  P1 partials
+//   stage 2  thread (slot, k): t1[slot][k*L2 .. (k+1)*L2)                                   -> t2[slot][k],  P2 partials
+//   stage 3  thread slot:      sum of t2[slot][0..P2)                                       -> rc[slot]
+// Slots are enumerated in the rc layout (slot = (2*dom + which) * NR + idx); unused column slots produce infinity.
+constexpr int RC_L1 = 16, RC_L2 = 8;
 template <class F>
-__global__ void __launch_bounds__(RED_T) k_rowcol_block(const XYZZ<F> *__restrict__ B, int N, int s, int n_dom, XYZZ<F> *__restrict__ rc) {
-    extern __shared__ unsigned char smraw[];
-    XYZZ<F> *sm = reinterpret_cast<XYZZ<F> *>(smraw);
+__global__ void __launch_bounds__(RED_T) k_rowcol_stage1(const XYZZ<F> *__restrict__ B, int N, int s, int n_dom, int P1, XYZZ<F> *__restrict__ t1) {
     const int S = 1 << s, nr = N >> s, nc = S - 1;
-    const int dom = blockIdx.x / (nr + nc), idx = blockIdx.x % (nr + nc);
+    // dense enumeration of the live (slot, run) pairs: all row runs first, then all column runs (t1 is pre-zeroed = infinity)
+    const int P1r = (S + RC_L1 - 1) / RC_L1, P1c = (nr + 1 + RC_L1 - 1) / RC_L1;
+    size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n_row = (size_t)n_dom * nr * P1r, n_col = (size_t)n_dom * nc * P1c;
+    if (id >= n_row + n_col) return;
+    int dom, idx, k, which;
+    if (id < n_row) { which = 0; k = (int)(id % P1r); size_t q = id / P1r; idx = (int)(q % nr); dom = (int)(q / nr); }
+    else { id -= n_row; which = 1; k = (int)(id % P1c); size_t q = id / P1c; idx = (int)(q % nc); dom = (int)(q / nc); }
     const XYZZ<F> *p = B + (size_t)dom * N;
     XYZZ<F> acc = XYZZ<F>::inf();
-    if (idx < nr) {
-        int hi = idx + 1;
-        for (int lo = threadIdx.x; lo < S; lo += RED_T) { int d = hi * S + lo; if (d <= N) acc.add(p[d - 1]); }
+    if (which == 0) {
+        int hi = idx + 1, lo1 = (k + 1) * RC_L1 < S ? (k + 1) * RC_L1 : S;
+        for (int lo = k * RC_L1; lo < lo1; lo++) { int d = hi * S + lo; if (d <= N) acc.add(p[d - 1]); }
     } else {
-        int lo = idx - nr + 1;
-        for (int hi = threadIdx.x; hi <= nr; hi += RED_T) { int d = hi * S + lo; if (d <= N) acc.add(p[d - 1]); }
+        int lo = idx + 1, h1 = (k + 1) * RC_L1 < nr + 1 ? (k + 1) * RC_L1 : nr + 1;
+        for (int hi = k * RC_L1; hi < h1; hi++) { int d = hi * S + lo; if (d <= N) acc.add(p[d - 1]); }
     }
-    sm[threadIdx.x] = acc;
-    __syncthreads();
-    for (int o = RED_T >> 1; o > 0; o >>= 1) {
-        if ((int)threadIdx.x < o) { XYZZ<F> x = sm[threadIdx.x]; x.add(sm[threadIdx.x + o]); sm[threadIdx.x] = x; }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        if (idx < nr) rc[((size_t)2 * dom) * nr + idx] = sm[0]; else rc[((size_t)2 * dom + 1) * nr + (idx - nr)] = sm[0];
-    }
+    t1[((size_t)(2 * dom + which) * nr + idx) * P1 + k] = acc;
+}
+// out[g][k] = sum in[g][k*L .. min((k+1)*L, P_in));  P_out = ceil(P_in / L)
+template <class F>
+__global__ void __launch_bounds__(RED_T) k_seg_sums(const XYZZ<F> *__restrict__ in, size_t n_groups, int P_in, int L, int P_out, XYZZ<F> *__restrict__ out) {
+    size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n_groups * P_out) return;
+    const size_t g = id / P_out; const int k = (int)(id % P_out);
+    const XYZZ<F> *p = in + g * P_in;
+    int j1 = (k + 1) * L < P_in ? (k + 1) * L : P_in;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (int j = k * L; j < j1; j++) acc.add(p[j]);
+    out[id] = acc;
 }
 // thread per domain: R = 2^s * Rrc[2 dom] + Rrc[2 dom + 1]
 template <class F>

@@ -184,12 +184,24 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
         XYZZ<F> *rc = ctx->red_rows.as<XYZZ<F>>(), *Rrc = R + n_dom + 1;
         if (sm_warp > 48 * 1024) {
             ZK_CUDA(cudaFuncSetAttribute(k_rowcol_sums<F, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_warp));
-            ZK_CUDA(cudaFuncSetAttribute(k_rowcol_block<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_warp));
         }
         size_t n_items = n_dom * (size_t)(nr + nc);
-        ZK_CUDA(cudaMemsetAsync(rc, 0, 2 * n_dom * (size_t)nr * pt, st));          // infinity padding of the column halves
-        if (n_dom >= 8) k_rowcol_sums<F, 8><<<(unsigned)((((n_items + 3) / 4) * 32 + RED_T - 1) / RED_T), RED_T, sm_warp, st>>>(buckets, nbins, s, (int)n_dom, rc);
-        else k_rowcol_block<F><<<(unsigned)n_items, RED_T, sm_warp, st>>>(buckets, nbins, s, (int)n_dom, rc);
+        if (n_dom >= 8) {
+            ZK_CUDA(cudaMemsetAsync(rc, 0, 2 * n_dom * (size_t)nr * pt, st));      // infinity padding of the column halves
+            k_rowcol_sums<F, 8><<<(unsigned)((((n_items + 3) / 4) * 32 + RED_T - 1) / RED_T), RED_T, sm_warp, st>>>(buckets, nbins, s, (int)n_dom, rc);
+        } else {
+            const size_t n_slots = 2 * n_dom * (size_t)nr;
+            const int longest = (1 << s) > nr + 1 ? (1 << s) : nr + 1;
+            const int P1 = (longest + RC_L1 - 1) / RC_L1, P2 = (P1 + RC_L2 - 1) / RC_L2;
+            ZK_TRY(ctx->red_tmp.reserve(n_slots * (size_t)(P1 + P2) * pt));
+            XYZZ<F> *t1 = ctx->red_tmp.as<XYZZ<F>>(), *t2 = t1 + n_slots * P1;
+            const int P1r = ((1 << s) + RC_L1 - 1) / RC_L1, P1c = (nr + 1 + RC_L1 - 1) / RC_L1;
+            const size_t live = n_dom * ((size_t)nr * P1r + (size_t)nc * P1c);
+            ZK_CUDA(cudaMemsetAsync(t1, 0, n_slots * (size_t)P1 * pt, st));
+            k_rowcol_stage1<F><<<(unsigned)((live + RED_T - 1) / RED_T), RED_T, 0, st>>>(buckets, nbins, s, (int)n_dom, P1, t1);
+            k_seg_sums<F><<<(unsigned)((n_slots * P2 + RED_T - 1) / RED_T), RED_T, 0, st>>>(t1, n_slots, P1, RC_L2, P2, t2);
+            k_seg_sums<F><<<(unsigned)((n_slots + RED_T - 1) / RED_T), RED_T, 0, st>>>(t2, n_slots, P2, P2, 1, rc);
+        }
         bit_reduce(rc, nr, c - s, 2 * n_dom, Rrc);      // rows: hi in [1, 2^(c-1-s)] (c-s bits); columns: lo in [1, 2^s - 1]
         k_join_rowcol<F><<<(unsigned)((n_dom + 63) / 64), 64, 0, st>>>(Rrc, s, (int)n_dom, R);
     } else if (tables) {
