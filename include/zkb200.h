@@ -41,6 +41,7 @@ extern "C" {
 #define ZK_ERR_IO (-6)                   /* SynthesisError::IoError: truncated / malformed Parameters stream */
 #define ZK_ERR_DECODE (-7)               /* GroupDecodingError (not on curve, not in subgroup, bad flags, x >= q) */
 #define ZK_ERR_NOT_CANONICAL (-8)        /* a scalar >= r (PrimeFieldDecodingError::NotInField) */
+#define ZK_ERR_MALFORMED_VK (-9)         /* SynthesisError::MalformedVerifyingKey: inputs.len() + 1 != ic.len() */
 
 const char *zk_last_error(void);
 int zk_device_count(void);
@@ -159,6 +160,36 @@ int zk_bench_modmul(zk_ctx *ctx, int field, int blocks, int threads, int iters, 
  * count (bench.py's roofline block).  Disabled by default (no events are created). */
 int zk_ctx_profile(zk_ctx *ctx, int enable);
 int zk_ctx_profile_read(zk_ctx *ctx, double *total_ms, uint64_t *launches);
+
+/* ---- Groth16 verification (the step after the proving path) ----------------------------------
+ * zk_pvk: bellman_verifier::PreparedVerifyingKey<Bls12> resident on the device — e(alpha_g1, beta_g2), the Miller-loop
+ * line coefficients of -gamma_g2 and -delta_g2, ic, and a fixed-base table of ic[1..] for the public-input sums. */
+typedef struct zk_pvk zk_pvk;
+/* PreparedVerifyingKey::read (core/bellman-verifier/src/lib.rs:204-245): the bytes zface ships as conf_vk.dat /
+ * anony_vk.dat and modules/zk-system keeps in storage.  ic points are checked (on curve, subgroup, not infinity). */
+int zk_pvk_load(zk_ctx *ctx, const uint8_t *pvk_bytes, size_t len, zk_pvk **out);
+/* prepare_verifying_key(&vk) (core/bellman-verifier/src/verifier.rs:15-30) computed on the device from the VerifyingKey
+ * encoding (alpha_g1 | beta_g1 | beta_g2 | gamma_g2 | delta_g1 | delta_g2 | u32 n | ic) — the head of Parameters::write,
+ * so a proving-key buffer can be passed as is (trailing bytes are ignored). */
+int zk_pvk_prepare(zk_ctx *ctx, const uint8_t *vk_bytes, size_t len, zk_pvk **out);
+/* PreparedVerifyingKey::write (lib.rs:183-202): zk_pvk_size bytes, byte-identical to the reference's file */
+size_t zk_pvk_size(const zk_pvk *k);
+int zk_pvk_write(const zk_pvk *k, uint8_t *out);
+size_t zk_pvk_num_inputs(const zk_pvk *k);      /* ic.len() - 1 */
+void zk_pvk_free(zk_pvk *k);
+/* Proof::read (lib.rs:67-108) + verify_proof (verifier.rs:32-63) for n proofs against one key.
+ * proofs: n * 192 bytes (Proof::write); inputs: n * n_inputs canonical Fr (4 LE u64 each, FrRepr);
+ * verdicts[i]: 1 = Ok(true), 0 = Ok(false), 2 = Proof::read failed with InvalidData (bad flags, x >= q, not on curve,
+ * not in the subgroup), 3 = Proof::read failed with PointInfinity.  Returns ZK_ERR_MALFORMED_VK when
+ * n_inputs + 1 != ic.len(), ZK_ERR_NOT_CANONICAL when an input is >= r. */
+int zk_groth16_verify_batch(zk_ctx *ctx, const zk_pvk *k, size_t n, const uint8_t *proofs, const uint64_t *inputs,
+                            size_t n_inputs, uint8_t *verdicts);
+/* same with device pointers; asynchronous on the context's stream (zk_ctx_sync reports a pending ZK_ERR_NOT_CANONICAL) */
+int zk_groth16_verify_batch_device(zk_ctx *ctx, const zk_pvk *k, size_t n, const uint8_t *d_proofs, const uint64_t *d_inputs,
+                                   size_t n_inputs, uint8_t *d_verdicts);
+/* Engine::pairing (core/pairing/src/lib.rs:108-115, bls12_381/mod.rs:40-160) for n pairs of checked G1Uncompressed /
+ * G2Uncompressed encodings; out: n * 576 bytes in Fq12::write order (fq12.rs:29-45). */
+int zk_pairing_batch(zk_ctx *ctx, size_t n, const uint8_t *g1, const uint8_t *g2, uint8_t *out);
 
 #ifdef __cplusplus
 }

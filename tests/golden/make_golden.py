@@ -85,6 +85,15 @@ def main():
     res["pairing_kat"] = {"alpha_g1_uncompressed": pk[0:96].hex(), "beta_g2_uncompressed": pk[192:384].hex(),
                           "alpha_g1_beta_g2_fq12": vk[0:576].hex(),
                           "source": "zface/params/conf_pk.dat[0:96], [192:384]; zface/params/conf_vk.dat[0:576]"}
+    # verifier fixtures (binary, small): the shipped PreparedVerifyingKey files and the VerifyingKey head of the matching
+    # proving keys (Parameters::write starts with vk: 868 bytes + 96 per ic point).  prepare_verifying_key of the latter
+    # must reproduce the former byte for byte (tests/test_oracle_pairing.py, tests/test_gpu_verify.py).
+    here = os.path.dirname(os.path.abspath(__file__))
+    for name in ("conf", "anony"):
+        pkb = open(os.path.join(REF, "zface/params/%s_pk.dat" % name), "rb").read()
+        n_ic = int.from_bytes(pkb[864:868], "big")
+        open(os.path.join(here, "%s_vk_head.bin" % name), "wb").write(pkb[:868 + 96 * n_ic])
+        open(os.path.join(here, "%s_pvk.dat" % name), "wb").write(open(os.path.join(REF, "zface/params/%s_vk.dat" % name), "rb").read())
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "kats.json")
     json.dump(res, open(out, "w"), indent=1)
     print("wrote", out, {k: len(v["groups"]) for k, v in res["tests"].items()})

@@ -57,3 +57,65 @@ def test_oracle_proof_verifies_and_tampered_fails():
     assert not pr.groth16_verify(vk, proof_points(proof), [z[1], z[2], (z[3] + 1) % pr.R])        # wrong public input
     A, B, C = proof_points(proof)
     assert not pr.groth16_verify(vk, (A, B, pr.ec_add(pr.FQ, C, pr.G1_GEN)), z[1:4])               # tampered C
+
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("name", ["conf", "anony"])
+def test_prepared_verifying_key_matches_shipped_file(name):
+    """prepare_verifying_key (verifier.rs:15-30) + PreparedVerifyingKey::write (lib.rs:183-202) restated in the oracle
+    reproduce zface/params/{conf,anony}_vk.dat from the VerifyingKey inside the matching proving key — pins g2_prepare's
+    line coefficients (scaling included), the Fq12 encoding and the pairing value."""
+    vk = pr.vk_read(open(os.path.join(GOLD, "%s_vk_head.bin" % name), "rb").read())
+    want = open(os.path.join(GOLD, "%s_pvk.dat" % name), "rb").read()
+    assert pr.pvk_write(vk) == want
+
+
+def test_prepared_verifier_agrees_with_plain_verifier():
+    shape = dict(n_constraints=40, n_inputs=3, n_aux=30, a_aux_density=25, b_density=20)
+    r1cs = sy.make_r1cs(seed=5, **shape)
+    crs = sy.make_toy_crs(r1cs, co.g1_fixed_base, co.g2_fixed_base, seed=6)
+    z = sy.make_witness(r1cs, 2)
+    a, b, c = sy.evaluate(r1cs, z)
+    P = co.Params(crs.params_bytes, checked=True)
+    proof = P.prove(co.ints_to_limbs(a, 4), co.ints_to_limbs(b, 4), co.ints_to_limbs(c, 4), co.ints_to_limbs(z[:3], 4),
+                    co.ints_to_limbs(z[3:], 4), *sy.densities(r1cs), 77, 99)
+    vk = pr.vk_read(crs.params_bytes)
+    ab = pr.pairing_reference(vk["alpha_g1"], vk["beta_g2"])
+    gam, dlt = pr.g2_prepare(pr.ec_neg(pr.FQ2, vk["gamma_g2"])), pr.g2_prepare(pr.ec_neg(pr.FQ2, vk["delta_g2"]))
+    pts = pr.proof_read(proof)
+    assert pts == proof_points(proof)
+    assert pr.verify_prepared(ab, gam, dlt, vk["ic"], pts, z[1:3])
+    assert not pr.verify_prepared(ab, gam, dlt, vk["ic"], pts, [z[1], (z[2] + 1) % pr.R])
+    with pytest.raises(ValueError, match="MalformedVerifyingKey"):
+        pr.verify_prepared(ab, gam, dlt, vk["ic"], pts, z[1:2])
+
+
+def test_proof_read_rejections():
+    """Proof::read (lib.rs:67-108): InvalidData for bad encodings / off-curve / out-of-subgroup points, PointInfinity for O."""
+    good = pr.proof_bytes(pr.ec_mul(pr.FQ, pr.G1_GEN, 5), pr.ec_mul(pr.FQ2, pr.G2_GEN, 7), pr.ec_mul(pr.FQ, pr.G1_GEN, 11))
+    assert pr.proof_read(good)[0] == pr.ec_mul(pr.FQ, pr.G1_GEN, 5)
+    inf1 = bytes([0xC0]) + bytes(47)
+    with pytest.raises(ValueError, match="PointInfinity"):
+        pr.proof_read(inf1 + good[48:])
+    with pytest.raises(ValueError, match="InvalidData"):
+        pr.proof_read(bytes([good[0] & 0x7F]) + good[1:])                    # compression bit cleared
+    with pytest.raises(ValueError, match="InvalidData"):
+        pr.proof_read(bytes([0xC0]) + bytes(46) + b"\x01" + good[48:])       # infinity with stray bits
+    with pytest.raises(ValueError, match="InvalidData"):
+        pr.proof_read(bytes([0x9F]) + b"\xff" * 47 + good[48:])              # x >= q
+    # x with no point on the curve / a curve point outside the r-torsion
+    x = 1
+    while pr.FQ.sqrt((x ** 3 + 4) % pr.Q) is not None:
+        x += 1
+    with pytest.raises(ValueError, match="InvalidData"):
+        pr.proof_read(bytes([0x80 | (x >> 376)]) + (x & ((1 << 376) - 1)).to_bytes(47, "big") + good[48:])
+    x = 0
+    while True:
+        y = pr.FQ.sqrt((x ** 3 + 4) % pr.Q)
+        if y is not None and pr.ec_mul(pr.FQ, (x, y), pr.R) is not pr.INF:
+            break
+        x += 1
+    with pytest.raises(ValueError, match="InvalidData"):
+        pr.proof_read(pr.g1_compressed((x, y)) + good[48:])

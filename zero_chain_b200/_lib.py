@@ -46,6 +46,15 @@ SIGNATURES = {
     "zk_bench_modmul": (i32, [vp, i32, i32, i32, i32, C.POINTER(dbl), C.POINTER(dbl)]),
     "zk_ctx_profile": (i32, [vp, i32]),
     "zk_ctx_profile_read": (i32, [vp, C.POINTER(dbl), C.POINTER(C.c_uint64)]),
+    "zk_pvk_load": (i32, [vp, vp, sz, PP]),
+    "zk_pvk_prepare": (i32, [vp, vp, sz, PP]),
+    "zk_pvk_size": (sz, [vp]),
+    "zk_pvk_write": (i32, [vp, vp]),
+    "zk_pvk_num_inputs": (sz, [vp]),
+    "zk_pvk_free": (None, [vp]),
+    "zk_groth16_verify_batch": (i32, [vp, vp, sz, vp, vp, sz, vp]),
+    "zk_groth16_verify_batch_device": (i32, [vp, vp, sz, vp, vp, sz, vp]),
+    "zk_pairing_batch": (i32, [vp, sz, vp, vp, vp]),
 }
 
 _lib = None

@@ -54,6 +54,8 @@ struct zk_ctx {
     DevBuf ntt_tw, ntt_tmp;
     // groth16 workspace
     DevBuf g_a, g_b, g_c, g_h, g_scal, g_misc;
+    // verifier workspace (pairing.cu)
+    DevBuf v_pts, v_stat, v_coef, v_f, v_part, v_io;
     // live kernel timing (zk_ctx_profile): CUDA events around the dominant kernel on ctx->stream
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_events;   // pairs (start, stop)

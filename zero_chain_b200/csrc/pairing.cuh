@@ -20,6 +20,7 @@
 // Values are canonical Montgomery field elements throughout, so results are bit-identical to the reference's.
 #pragma once
 #include "curve.cuh"
+#include <stddef.h>
 #include "pairing_consts.inc"
 
 #ifdef ZK_HOST_EMUL
@@ -54,7 +55,7 @@ struct Fq6 {
     ZK_DEV Fq6 mul_v() const { Fq6 r; r.c0 = mul_xi(c2); r.c1 = c0; r.c2 = c1; return r; }   // v^3 = xi
 };
 // Karatsuba over the three Fq2 slots: 6 Fq2 products
-ZK_PTFN Fq6 mul6(const Fq6 &a, const Fq6 &b) {
+static ZK_PTFN Fq6 mul6(const Fq6 &a, const Fq6 &b) {
     Fq2 t0 = a.c0 * b.c0, t1 = a.c1 * b.c1, t2 = a.c2 * b.c2;
     Fq6 r;
     r.c0 = t0 + mul_xi((a.c1 + a.c2) * (b.c1 + b.c2) - t1 - t2);
@@ -63,7 +64,7 @@ ZK_PTFN Fq6 mul6(const Fq6 &a, const Fq6 &b) {
     return r;
 }
 // a * (b0 + b1 v): 5 Fq2 products
-ZK_PTFN Fq6 mul6_01(const Fq6 &a, const Fq2 &b0, const Fq2 &b1) {
+static ZK_PTFN Fq6 mul6_01(const Fq6 &a, const Fq2 &b0, const Fq2 &b1) {
     Fq2 t0 = a.c0 * b0, t1 = a.c1 * b1;
     Fq6 r;
     r.c0 = t0 + mul_xi(a.c2 * b1);
@@ -72,10 +73,10 @@ ZK_PTFN Fq6 mul6_01(const Fq6 &a, const Fq2 &b0, const Fq2 &b1) {
     return r;
 }
 // a * (b1 v): 3 Fq2 products
-ZK_PTFN Fq6 mul6_1(const Fq6 &a, const Fq2 &b1) {
+static ZK_PTFN Fq6 mul6_1(const Fq6 &a, const Fq2 &b1) {
     Fq6 r; r.c0 = mul_xi(a.c2 * b1); r.c1 = a.c0 * b1; r.c2 = a.c1 * b1; return r;
 }
-ZK_PTFN Fq6 inv6(const Fq6 &a) {
+static ZK_PTFN Fq6 inv6(const Fq6 &a) {
     // adjugate over Fq2: (A, B, C) / (a0 A + xi (a2 B + a1 C))
     Fq2 A = a.c0.sqr() - mul_xi(a.c1 * a.c2);
     Fq2 B = mul_xi(a.c2.sqr()) - a.c0 * a.c1;
@@ -93,33 +94,33 @@ struct Fq12 {
     // slot t of sum_t c_t w^t:  t = 2 j + i  <->  (w^i, v^j)
     ZK_DEV Fq2 &slot(int t) { Fq6 &h = (t & 1) ? c1 : c0; int j = t >> 1; return j == 0 ? h.c0 : j == 1 ? h.c1 : h.c2; }
 };
-ZK_PTFN Fq12 mul12(const Fq12 &a, const Fq12 &b) {
+static ZK_PTFN Fq12 mul12(const Fq12 &a, const Fq12 &b) {
     Fq6 t0 = mul6(a.c0, b.c0), t1 = mul6(a.c1, b.c1);
     Fq12 r;
     r.c1 = mul6(a.c0 + a.c1, b.c0 + b.c1) - t0 - t1;
     r.c0 = t0 + t1.mul_v();
     return r;
 }
-ZK_PTFN Fq12 sqr12(const Fq12 &a) {
+static ZK_PTFN Fq12 sqr12(const Fq12 &a) {
     Fq6 ab = mul6(a.c0, a.c1);
     Fq12 r;
     r.c0 = mul6(a.c0 + a.c1, a.c0 + a.c1.mul_v()) - ab - ab.mul_v();
     r.c1 = ab + ab;
     return r;
 }
-ZK_PTFN Fq12 inv12(const Fq12 &a) {   // 1 / (c0 + c1 w) = (c0 - c1 w) / (c0^2 - v c1^2)
+static ZK_PTFN Fq12 inv12(const Fq12 &a) {   // 1 / (c0 + c1 w) = (c0 - c1 w) / (c0^2 - v c1^2)
     Fq6 n = inv6(mul6(a.c0, a.c0) - mul6(a.c1, a.c1).mul_v());
     Fq12 r; r.c0 = mul6(a.c0, n); r.c1 = mul6(a.c1, n).neg(); return r;
 }
 // f * (c2 + (c1) v + (c0) v w) with the Fq scalings of ell() already applied by the caller: 13 Fq2 products
-ZK_PTFN Fq12 mul12_014(const Fq12 &f, const Fq2 &s0, const Fq2 &s1, const Fq2 &s4) {
+static ZK_PTFN Fq12 mul12_014(const Fq12 &f, const Fq2 &s0, const Fq2 &s1, const Fq2 &s4) {
     Fq6 t0 = mul6_01(f.c0, s0, s1), t1 = mul6_1(f.c1, s4);
     Fq12 r;
     r.c1 = mul6_01(f.c0 + f.c1, s0, s1 + s4) - t0 - t1;
     r.c0 = t0 + t1.mul_v();
     return r;
 }
-ZK_PTFN Fq12 frobenius12(const Fq12 &a, int k) {
+static ZK_PTFN Fq12 frobenius12(const Fq12 &a, int k) {
     Fq2 g = frob_gamma(k), gp = g;
     Fq12 r = a;
     for (int t = 0; t < 6; t++) {
@@ -132,7 +133,7 @@ ZK_PTFN Fq12 frobenius12(const Fq12 &a, int k) {
     return r;
 }
 // f^|x| by square-and-multiply, then conjugated: f^x for f in the cyclotomic subgroup
-ZK_PTFN Fq12 exp_x(const Fq12 &f) {
+static ZK_PTFN Fq12 exp_x(const Fq12 &f) {
     Fq12 r = f;
     for (int i = 62; i >= 0; i--) {
         r = sqr12(r);
@@ -141,7 +142,7 @@ ZK_PTFN Fq12 exp_x(const Fq12 &f) {
     return r.conj();
 }
 // returns false when f == 0 (Engine::final_exponentiation -> None)
-ZK_PTFN bool final_exponentiation(const Fq12 &f, Fq12 &out) {
+static ZK_PTFN bool final_exponentiation(const Fq12 &f, Fq12 &out) {
     if (f.is_zero()) return false;
     Fq12 g = mul12(f.conj(), inv12(f));                  // f^(q^6 - 1)
     g = mul12(frobenius12(g, 2), g);                      // ^(q^2 + 1): now in the cyclotomic subgroup, inverse = conj
@@ -158,7 +159,7 @@ ZK_PTFN bool final_exponentiation(const Fq12 &f, Fq12 &out) {
 struct LineCoeff { Fq2 c0, c1, c2; };
 struct G2Jac { Fq2 x, y, z; };
 
-ZK_PTFN LineCoeff doubling_step(G2Jac &t) {
+static ZK_PTFN LineCoeff doubling_step(G2Jac &t) {
     Fq2 xx = t.x.sqr(), yy = t.y.sqr(), zz = t.z.sqr();
     Fq2 s = (t.x * yy).dbl().dbl();                       // 4 X Y^2
     Fq2 e = xx.dbl() + xx;                                // 3 X^2
@@ -172,7 +173,7 @@ ZK_PTFN LineCoeff doubling_step(G2Jac &t) {
     t.x = x3; t.y = y3; t.z = z3;
     return l;
 }
-ZK_PTFN LineCoeff addition_step(G2Jac &t, const Affine<Fq2> &q) {
+static ZK_PTFN LineCoeff addition_step(G2Jac &t, const Affine<Fq2> &q) {
     Fq2 zz = t.z.sqr();
     Fq2 h = q.x * zz - t.x;
     Fq2 r = (q.y * (t.z * zz) - t.y).dbl();
@@ -190,7 +191,7 @@ ZK_PTFN LineCoeff addition_step(G2Jac &t, const Affine<Fq2> &q) {
     return l;
 }
 // coefficient order = consumption order of the Miller loop; `stride` separates consecutive coefficients in `out`
-ZK_PTFN void g2_prepare(const Affine<Fq2> &q, LineCoeff *out, size_t stride) {
+static ZK_PTFN void g2_prepare(const Affine<Fq2> &q, LineCoeff *out, size_t stride) {
     G2Jac t; t.x = q.x; t.y = q.y; t.z = Fq2::one();
     int n = 0;
     for (int i = 62; i >= 1; i--) {
@@ -203,7 +204,7 @@ ZK_DEV Fq12 ell(const Fq12 &f, const LineCoeff &c, const Affine<Fq> &p) {
     return mul12_014(f, c.c2, mul_fq(c.c1, p.x), mul_fq(c.c0, p.y));
 }
 // one pair; infinity on either side contributes 1 (mod.rs:50-54)
-ZK_PTFN Fq12 miller_loop(const Affine<Fq> &p, const LineCoeff *coeffs, size_t stride, bool g2_inf) {
+static ZK_PTFN Fq12 miller_loop(const Affine<Fq> &p, const LineCoeff *coeffs, size_t stride, bool g2_inf) {
     Fq12 f = Fq12::one();
     if (p.is_inf() || g2_inf) return f;
     int n = 0;

@@ -28,7 +28,7 @@ R_MODULUS = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
 class SynthesisError(Exception):
     """bellman::SynthesisError variants reachable from the prover path."""
     NAMES = {-3: "AssignmentMissing", -4: "PolynomialDegreeTooLarge", -5: "UnexpectedIdentity", -6: "IoError",
-             -7: "IoError(GroupDecodingError)", -8: "IoError(NotInField)"}
+             -7: "IoError(GroupDecodingError)", -8: "IoError(NotInField)", -9: "MalformedVerifyingKey"}
 
     def __init__(self, code, msg):
         super().__init__("%s: %s" % (self.NAMES.get(code, "Error(%d)" % code), msg))
@@ -194,6 +194,86 @@ class Parameters:
             self.free()
         except Exception:
             pass
+
+
+class PreparedVerifyingKey:
+    """bellman_verifier::PreparedVerifyingKey<Bls12> on the device (core/bellman-verifier/src/lib.rs:110-245)."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx, self._h = ctx, handle
+        self.num_inputs = int(_lib.lib().zk_pvk_num_inputs(handle))
+
+    @staticmethod
+    def read(ctx: Context, buf: bytes) -> "PreparedVerifyingKey":
+        """PreparedVerifyingKey::read — the bytes of zface/params/conf_vk.dat."""
+        b = np.frombuffer(buf, np.uint8)
+        h = C.c_void_p()
+        _ck(_lib.lib().zk_pvk_load(ctx._h, _p(b), len(buf), C.byref(h)))
+        return PreparedVerifyingKey(ctx, h)
+
+    @staticmethod
+    def prepare(ctx: Context, vk_bytes: bytes) -> "PreparedVerifyingKey":
+        """prepare_verifying_key(&vk) (verifier.rs:15-30); vk_bytes = VerifyingKey encoding / head of Parameters::write."""
+        b = np.frombuffer(vk_bytes, np.uint8)
+        h = C.c_void_p()
+        _ck(_lib.lib().zk_pvk_prepare(ctx._h, _p(b), len(vk_bytes), C.byref(h)))
+        return PreparedVerifyingKey(ctx, h)
+
+    def write(self) -> bytes:
+        out = np.zeros(int(_lib.lib().zk_pvk_size(self._h)), np.uint8)
+        _ck(_lib.lib().zk_pvk_write(self._h, _p(out)))
+        return out.tobytes()
+
+    def free(self):
+        if self._h:
+            _lib.lib().zk_pvk_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+VERDICT_OK, VERDICT_FALSE, VERDICT_INVALID_DATA, VERDICT_POINT_INFINITY = 1, 0, 2, 3
+
+
+def verify_proofs(pvk: PreparedVerifyingKey, proofs: bytes, public_inputs) -> list:
+    """Proof::read + verify_proof (verifier.rs:32-63) for len(proofs)/192 proofs; public_inputs: one list of ints per
+    proof (without the leading ONE).  Returns the verdict codes of include/zkb200.h; raises
+    SynthesisError(MalformedVerifyingKey) when the input count does not match the key."""
+    n = len(proofs) // 192
+    assert len(proofs) == 192 * n and len(public_inputs) == n
+    n_in = len(public_inputs[0]) if n else pvk.num_inputs
+    assert all(len(x) == n_in for x in public_inputs)
+    inp = _u64([_fr_limbs(v) for row in public_inputs for v in row]) if n * n_in else np.zeros(1, np.uint64)
+    pb = np.frombuffer(proofs, np.uint8) if n else np.zeros(1, np.uint8)
+    out = np.zeros(max(n, 1), np.uint8)
+    _ck(_lib.lib().zk_groth16_verify_batch(pvk.ctx._h, pvk._h, n, _p(pb), _p(inp), n_in, _p(out)))
+    return [int(v) for v in out[:n]]
+
+
+def verify_proof(pvk: PreparedVerifyingKey, proof: bytes, public_inputs) -> bool:
+    """verify_proof(pvk, proof, inputs) -> Ok(bool); a proof that Proof::read rejects raises ZkError (io::Error there)."""
+    v = verify_proofs(pvk, proof, [list(public_inputs)])[0]
+    if v >= 2:
+        raise ZkError(-7, "Proof::read: %s" % ("PointInfinity" if v == 3 else "InvalidData"))
+    return v == 1
+
+
+def verify_proofs_device(pvk: PreparedVerifyingKey, n: int, d_proofs_ptr: int, d_inputs_ptr: int, n_inputs: int, d_verdicts_ptr: int):
+    _ck(_lib.lib().zk_groth16_verify_batch_device(pvk.ctx._h, pvk._h, n, C.c_void_p(d_proofs_ptr), C.c_void_p(d_inputs_ptr), n_inputs,
+                                                  C.c_void_p(d_verdicts_ptr)))
+
+
+def pairing(ctx: Context, g1_uncompressed: bytes, g2_uncompressed: bytes) -> bytes:
+    """Engine::pairing for len/96 pairs; 576 bytes each in Fq12::write order."""
+    n = len(g1_uncompressed) // 96
+    assert len(g1_uncompressed) == 96 * n and len(g2_uncompressed) == 192 * n
+    out = np.zeros(576 * max(n, 1), np.uint8)
+    _ck(_lib.lib().zk_pairing_batch(ctx._h, n, _p(np.frombuffer(g1_uncompressed, np.uint8)), _p(np.frombuffer(g2_uncompressed, np.uint8)), _p(out)))
+    return out[:576 * n].tobytes()
 
 
 class ProvingAssignment:
