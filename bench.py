@@ -390,13 +390,86 @@ def prove_metrics(ctx, zk, sy, args, batch=256, steps=3, cpu=True):
         cpu_block = {"value": 1.0 / cpu_dt, "unit": "proofs/s", "cores": co.num_threads(), "kind": "port",
                      "sample": "oracle create_proof, best of 2, same CRS/witness", "matches_gpu_proof_bytes": True}
     params.free()
+    try:
+        verify_block = verify_metrics(ctx, zk, crs.params_bytes, proofs, np.ascontiguousarray(views[3][:, 1:, :]), cpu)
+    except SystemExit:
+        raise
+    except Exception as e:
+        verify_block = {"error": repr(e)}
     return {"metric": "proofs_per_sec (confidential_transfer shape: 19974 constraints, 23 inputs, domain 2^15; synthetic R1CS, toy CRS)",
             "e2e_proofs_per_sec": batch / dt, "batch": batch, "steps": steps, "ms_per_batch": dt * 1e3, "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": 192 * batch, "single_proof_latency_ms": lat * 1e3, "params_load_checked_s": load_s,
             "from_witness": {"e2e_proofs_per_sec": batch / dt_w, "ms_per_batch": dt_w * 1e3, "h2d_bytes_per_step": int(h2d_w),
                              "api": "zk_groth16_prove_witness_batch (constraint system resident, GPU evaluates the R1CS rows)"},
-            "cpu_baseline": cpu_block,
+            "cpu_baseline": cpu_block, "verify": verify_block,
             "timing": "host wall clock around synchronous C-ABI calls (each call ends with a stream synchronise)"}
+
+
+def verify_metrics(ctx, zk, vk_bytes, proofs, inputs, cpu=True, n_v=8192):
+    """verifications/sec: the proofs the prover just made, replicated to a block-import sized batch, through
+    zk_groth16_verify_batch (host buffers: H2D of proofs + public inputs, D2H of the verdicts inside the timed region) and
+    zk_groth16_verify_batch_device (resident inputs, CUDA events on the library's stream); CPU: the oracle's verify_proof."""
+    import torch
+    import ctypes as C
+    from zero_chain_b200 import _lib
+    L = _lib.lib()
+    t = time.perf_counter()
+    pvk = zk.PreparedVerifyingKey.prepare(ctx, vk_bytes)
+    prep_s = time.perf_counter() - t
+    batch = len(proofs) // 192
+    n_in = inputs.shape[1]
+    reps = (n_v + batch - 1) // batch
+    pb = np.tile(np.frombuffer(proofs, np.uint8), reps)[:192 * n_v].copy()
+    inp = np.tile(inputs.reshape(batch, -1), (reps, 1))[:n_v].copy()
+    hp, hi = torch.from_numpy(pb).pin_memory(), torch.from_numpy(inp.view(np.int64)).pin_memory()
+    out = np.zeros(n_v, np.uint8)
+    call = lambda: zk._ck(L.zk_groth16_verify_batch(ctx._h, pvk._h, n_v, C.c_void_p(hp.data_ptr()), C.c_void_p(hi.data_ptr()), n_in,
+                                                    out.ctypes.data_as(C.c_void_p)))
+    call()
+    best = 1e9
+    for _ in range(3):
+        t = time.perf_counter(); call(); best = min(best, time.perf_counter() - t)
+    if not (out == 1).all():
+        raise SystemExit("PARITY FAILURE: the GPU verifier rejected a proof made by the GPU prover")
+    dp, di = hp.cuda(), hi.cuda()
+    dv = torch.zeros(n_v, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.ExternalStream(ctx.stream)
+    torch.cuda.synchronize()
+    dev = lambda: zk.verify_proofs_device(pvk, n_v, dp.data_ptr(), di.data_ptr(), n_in, dv.data_ptr())
+    dev(); ctx.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(3):
+        dev()
+    e1.record(stream)
+    ctx.sync(); torch.cuda.synchronize()
+    ms_dev = e0.elapsed_time(e1) / 3
+    assert bool((dv == 1).all())
+    # a tampered copy: one public input bumped in every 5th proof -> exactly those are rejected
+    bad = inp.copy(); bad[::5, 0] ^= 1
+    hb = torch.from_numpy(bad.view(np.int64))
+    zk._ck(L.zk_groth16_verify_batch(ctx._h, pvk._h, n_v, C.c_void_p(hp.data_ptr()), C.c_void_p(hb.data_ptr()), n_in, out.ctypes.data_as(C.c_void_p)))
+    want = np.ones(n_v, np.uint8); want[::5] = 0
+    if not (out == want).all():
+        raise SystemExit("PARITY FAILURE: the GPU verifier accepted a proof with a wrong public input")
+    cpu_block = None
+    if cpu:
+        from oracle import coracle as co
+        k = co.PreparedVerifyingKey.prepare(vk_bytes)
+        if k.write() != pvk.write():
+            raise SystemExit("PARITY FAILURE: prepared verifying key differs from the oracle's")
+        n_c = 8 * co.num_threads()
+        t = time.perf_counter(); v = k.verify_batch(pb[:192 * n_c].tobytes(), bad[:n_c], n_in); cpu_dt = time.perf_counter() - t
+        if v != [int(x) for x in want[:n_c]]:
+            raise SystemExit("PARITY FAILURE: oracle verdicts differ from the GPU's")
+        cpu_block = {"value": n_c / cpu_dt, "unit": "verifications/s", "cores": co.num_threads(), "kind": "port",
+                     "sample": "%d proofs (every 5th with a wrong input), oracle/pairing_oracle.inc verify_proof, %.2f s" % (n_c, cpu_dt),
+                     "matches_gpu_verdicts": True}
+    pvk.free()
+    return {"metric": "verifications_per_sec (Proof::read + verify_proof, %d public inputs, one prepared key)" % n_in, "batch": n_v,
+            "e2e_verifications_per_sec": n_v / best, "e2e_ms_per_batch": best * 1e3, "h2d_bytes_per_step": int(pb.nbytes + inp.nbytes),
+            "d2h_bytes_per_step": n_v, "device_verifications_per_sec": n_v / (ms_dev * 1e-3), "device_ms_per_batch": ms_dev,
+            "prepare_verifying_key_s": prep_s, "cpu_baseline": cpu_block}
 
 
 def run_reference(args):

@@ -289,3 +289,61 @@ def num_threads() -> int:
 
 def set_num_threads(n: int):
     lib().zko_set_num_threads(int(n))
+
+
+# ---- verifier side (oracle/pairing_oracle.inc) ----------------------------------------------------------------
+class PreparedVerifyingKey:
+    """PreparedVerifyingKey<Bls12> in the C oracle: `prepare` = prepare_verifying_key(vk) (verifier.rs:15-30) from the
+    VerifyingKey encoding, `read` = PreparedVerifyingKey::read (lib.rs:204-245)."""
+
+    def __init__(self, h):
+        self._h = h
+
+    @staticmethod
+    def prepare(vk_bytes: bytes) -> "PreparedVerifyingKey":
+        h = C.c_void_p()
+        b = np.frombuffer(vk_bytes, np.uint8)
+        r = lib().zko_pvk_prepare(_p(b), C.c_size_t(len(vk_bytes)), C.byref(h))
+        if r:
+            raise ValueError("zko_pvk_prepare: %d" % r)
+        return PreparedVerifyingKey(h)
+
+    @staticmethod
+    def read(buf: bytes) -> "PreparedVerifyingKey":
+        h = C.c_void_p()
+        b = np.frombuffer(buf, np.uint8)
+        r = lib().zko_pvk_read(_p(b), C.c_size_t(len(buf)), C.byref(h))
+        if r:
+            raise ValueError("zko_pvk_read: %d" % r)
+        return PreparedVerifyingKey(h)
+
+    def write(self) -> bytes:
+        lib().zko_pvk_size.restype = C.c_size_t
+        o = np.zeros(lib().zko_pvk_size(self._h), np.uint8)
+        lib().zko_pvk_write(self._h, _p(o))
+        return o.tobytes()
+
+    def verify_batch(self, proofs: bytes, inputs_limbs, n_inputs: int):
+        """verdicts per proof: 1 Ok(true), 0 Ok(false), 2 InvalidData, 3 PointInfinity; ValueError on MalformedVerifyingKey."""
+        n = len(proofs) // 192
+        pb = np.frombuffer(proofs, np.uint8) if n else np.zeros(1, np.uint8)
+        inp = _u64(inputs_limbs).reshape(-1) if n * n_inputs else np.zeros(4, np.uint64)
+        out = np.zeros(max(n, 1), np.uint8)
+        r = lib().zko_verify_batch(self._h, C.c_size_t(n), _p(pb), _p(inp), C.c_size_t(n_inputs), _p(out))
+        if r:
+            raise ValueError("MalformedVerifyingKey" if r == -9 else "zko_verify_batch: %d" % r)
+        return [int(v) for v in out[:n]]
+
+    def __del__(self):
+        try:
+            lib().zko_pvk_free(self._h)
+        except Exception:
+            pass
+
+
+def pairing(g1_uncompressed: bytes, g2_uncompressed: bytes) -> bytes:
+    o = np.zeros(576, np.uint8)
+    r = lib().zko_pairing(_p(np.frombuffer(g1_uncompressed, np.uint8)), _p(np.frombuffer(g2_uncompressed, np.uint8)), _p(o))
+    if r:
+        raise ValueError("zko_pairing: %d" % r)
+    return o.tobytes()

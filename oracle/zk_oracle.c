@@ -854,6 +854,9 @@ EXPORT int zko_groth16_prove(const zko_params *p,
     return 0;
 }
 
+/* ---- verifier side ---- */
+#include "pairing_oracle.inc"
+
 EXPORT int zko_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

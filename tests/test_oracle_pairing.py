@@ -119,3 +119,52 @@ def test_proof_read_rejections():
         x += 1
     with pytest.raises(ValueError, match="InvalidData"):
         pr.proof_read(pr.g1_compressed((x, y)) + good[48:])
+
+
+@pytest.mark.parametrize("name", ["conf", "anony"])
+def test_c_oracle_prepared_key_matches_shipped_file(name):
+    """The C restatement (oracle/pairing_oracle.inc: tower, G2Prepared, Miller loop, the reference's final-exponentiation
+    chain) against the same fixtures; it is the CPU baseline bench.py times and the checker of the big GPU batches."""
+    head = open(os.path.join(GOLD, "%s_vk_head.bin" % name), "rb").read()
+    want = open(os.path.join(GOLD, "%s_pvk.dat" % name), "rb").read()
+    assert co.PreparedVerifyingKey.prepare(head).write() == want
+    assert co.PreparedVerifyingKey.read(want).write() == want
+    assert co.pairing(head[0:96], head[192:384]) == want[:576]
+
+
+def test_c_oracle_verifier_agrees_with_pyref():
+    shape = dict(n_constraints=40, n_inputs=3, n_aux=30, a_aux_density=25, b_density=20)
+    r1cs = sy.make_r1cs(seed=5, **shape)
+    crs = sy.make_toy_crs(r1cs, co.g1_fixed_base, co.g2_fixed_base, seed=6)
+    P = co.Params(crs.params_bytes, checked=True)
+    vk = pr.vk_read(crs.params_bytes)
+    k = co.PreparedVerifyingKey.prepare(crs.params_bytes)
+    assert k.write() == pr.pvk_write(vk)
+    ab = pr.pairing_reference(vk["alpha_g1"], vk["beta_g2"])
+    gam, dlt = pr.g2_prepare(pr.ec_neg(pr.FQ2, vk["gamma_g2"])), pr.g2_prepare(pr.ec_neg(pr.FQ2, vk["delta_g2"]))
+    proofs, inputs = [], []
+    for seed in (1, 2, 3):
+        z = sy.make_witness(r1cs, seed)
+        a, b, c = sy.evaluate(r1cs, z)
+        proofs.append(P.prove(co.ints_to_limbs(a, 4), co.ints_to_limbs(b, 4), co.ints_to_limbs(c, 4), co.ints_to_limbs(z[:3], 4),
+                              co.ints_to_limbs(z[3:], 4), *sy.densities(r1cs), 7 * seed, 9 * seed))
+        inputs.append(z[1:3])
+    A, B, Cc = pr.proof_read(proofs[0])
+    proofs += [proofs[0], pr.proof_bytes(A, B, pr.ec_add(pr.FQ, Cc, pr.G1_GEN)), bytes([0xC0]) + bytes(47) + proofs[0][48:],
+               bytes([proofs[0][0] & 0x7F]) + proofs[0][1:], proofs[0][:48] + pr.g2_compressed(pr.ec_neg(pr.FQ2, B)) + proofs[0][144:]]
+    inputs += [[inputs[0][0], (inputs[0][1] + 1) % pr.R], inputs[0], inputs[0], inputs[0], inputs[0]]
+    got = k.verify_batch(b"".join(proofs), co.ints_to_limbs([v for row in inputs for v in row], 4), 2)
+    want = []
+    for p, x in zip(proofs, inputs):
+        try:
+            want.append(int(pr.verify_prepared(ab, gam, dlt, vk["ic"], pr.proof_read(p), x)))
+        except ValueError as e:
+            want.append(3 if "PointInfinity" in str(e) else 2)
+    assert got == want == [1, 1, 1, 0, 0, 3, 2, 0]
+    with pytest.raises(ValueError, match="MalformedVerifyingKey"):
+        k.verify_batch(proofs[0], co.ints_to_limbs(inputs[0][:1], 4), 1)
+    # a second sqrt algorithm (pyref: norm method; C: Algorithm 9) must land on the same points
+    for kk in (3, 5, 1234567):
+        q = pr.ec_mul(pr.FQ2, pr.G2_GEN, kk)
+        pp = pr.proof_bytes(pr.ec_mul(pr.FQ, pr.G1_GEN, kk), q, pr.G1_GEN)
+        assert k.verify_batch(pp, co.ints_to_limbs(inputs[0], 4), 2) == [0]
