@@ -12,6 +12,7 @@ extern "C" {
 int emu_sizeof_fq12() { return (int)sizeof(Fq12); }
 int emu_sizeof_coeff() { return (int)sizeof(LineCoeff); }
 void emu_f12_mul(const uint32_t *a, const uint32_t *b, uint32_t *o) { st12(o, mul12(ld12(a), ld12(b))); }
+void emu_f12_cyc_sqr(const uint32_t *a, uint32_t *o) { st12(o, cyclotomic_sqr(ld12(a))); }
 void emu_f12_sqr(const uint32_t *a, uint32_t *o) { st12(o, sqr12(ld12(a))); }
 void emu_f12_inv(const uint32_t *a, uint32_t *o) { st12(o, inv12(ld12(a))); }
 void emu_f12_frob(const uint32_t *a, int k, uint32_t *o) { st12(o, frobenius12(ld12(a), k)); }
@@ -31,4 +32,7 @@ void emu_miller(const uint32_t *p, const uint32_t *coeffs, uint32_t *o) {
 // Compressed::into_affine: returns the DEC_* code; out = affine Montgomery limbs
 int emu_decode_g1c(const uint8_t *in, uint32_t *out) { Affine<Fq> p = Affine<Fq>::inf(); int e = zkcodec::decode_compressed(p, in); memcpy(out, &p, sizeof(p)); return e; }
 int emu_decode_g2c(const uint8_t *in, uint32_t *out) { Affine<Fq2> p = Affine<Fq2>::inf(); int e = zkcodec::decode_compressed(p, in); memcpy(out, &p, sizeof(p)); return e; }
+// subgroup tests on affine Montgomery limbs: bit 0 = endomorphism test, bit 1 = multiplication by r
+int emu_g1_subgroup(const uint32_t *in) { Affine<Fq> p; memcpy(&p, in, sizeof(p)); return (int)zkcodec::in_subgroup(p) | ((int)zkcodec::in_subgroup_by_order(p) << 1); }
+int emu_g2_subgroup(const uint32_t *in) { Affine<Fq2> p; memcpy(&p, in, sizeof(p)); return (int)zkcodec::in_subgroup(p) | ((int)zkcodec::in_subgroup_by_order(p) << 1); }
 }

@@ -82,8 +82,12 @@ def test_tower_arithmetic(emu):
         emu.emu_f12_mul(_p(A), _p(B), _p(o)); assert arr_f12(o) == pr._f12_mul(a, b)
         emu.emu_f12_sqr(_p(A), _p(o)); assert arr_f12(o) == pr._f12_mul(a, a)
         emu.emu_f12_inv(_p(A), _p(o)); assert pr._f12_mul(arr_f12(o), a) == pr.F12_ONE
+    # Granger-Scott squaring: valid exactly on the cyclotomic subgroup, i.e. after the easy part f^((q^6-1)(q^2+1))
+    g = pr._f12_pow(rand_f12(rng), (Q ** 6 - 1) * (Q ** 2 + 1))
+    emu.emu_f12_cyc_sqr(_p(f12_arr(g)), _p(o)); assert arr_f12(o) == pr._f12_mul(g, g)
     a = rand_f12(rng)
     A = f12_arr(a)
+    emu.emu_f12_cyc_sqr(_p(A), _p(o)); assert arr_f12(o) != pr._f12_mul(a, a)
     for k in (1, 2, 3):
         emu.emu_f12_frob(_p(A), k, _p(o))
         assert arr_f12(o) == pr._f12_pow(a, Q ** k)
@@ -159,3 +163,39 @@ def test_compressed_decode(emu):
     while pr.FQ2.sqrt(pr.FQ2.add(pr.FQ2.mul(pr.FQ2.mul(xx, xx), xx), pr.FQ2.b)) is not None:
         xx = (xx[0] + 1, 0)
     assert code(bytes([0x80]) + bytes(47) + xx[0].to_bytes(48, "big"), g2=True) == 4
+
+
+def test_subgroup_checks_by_endomorphism(emu):
+    """codec.cuh in_subgroup (phi / psi endomorphism tests) must agree with multiplication by r on members, on random curve
+    points, on points of the cofactor torsion ([r] Q) and on member + torsion sums."""
+    rng = pr.SplitMix64(404)
+
+    def rand_point(F):
+        while True:
+            x = rng.below(Q, 7) if F is pr.FQ else (rng.below(Q, 7), rng.below(Q, 7))
+            rhs = (x ** 3 + 4) % Q if F is pr.FQ else F.add(F.mul(F.mul(x, x), x), F.b)
+            y = F.sqrt(rhs)
+            if y is not None:
+                return (x, y)
+    for F, gen, arr, fn in ((pr.FQ, pr.G1_GEN, g1_arr, emu.emu_g1_subgroup), (pr.FQ2, pr.G2_GEN, g2_arr, emu.emu_g2_subgroup)):
+        for k in (1, 2, 3, pr.R - 1, rng.below(pr.R, 4), rng.below(pr.R, 4)):
+            assert fn(_p(arr(pr.ec_mul(F, gen, k)))) == 3
+        n_tors = 0
+        for _ in range(6):
+            p = rand_point(F)
+            assert fn(_p(arr(p))) == 0                                   # a random point is outside the subgroup
+            t = pr.ec_mul(F, p, pr.R)                                    # cofactor torsion
+            if t is not pr.INF:
+                n_tors += 1
+                assert fn(_p(arr(t))) == 0
+                assert fn(_p(arr(pr.ec_add(F, t, pr.ec_mul(F, gen, 5))))) == 0
+        assert n_tors
+    # small-order points: the G1 cofactor is divisible by 3 and 11 — points of exactly those orders
+    h1 = 0x396c8c005555e1568c00aaab0000aaab
+    for small, mult in ((3, 1), (11, 2)):                       # E(Fq) is not cyclic: its 11-part is (Z/11)^2, exponent 11
+        assert h1 % small ** mult == 0 and h1 % small ** (mult + 1) != 0
+        while True:
+            t = pr.ec_mul(pr.FQ, rand_point(pr.FQ), pr.R * (h1 // small ** mult))
+            if t is not pr.INF:
+                break
+        assert pr.ec_mul(pr.FQ, t, small) is pr.INF and emu.emu_g1_subgroup(_p(g1_arr(t))) == 0

@@ -7,6 +7,7 @@
 //   Fq2 wire order: c1 || c0
 #pragma once
 #include "curve.cuh"
+#include "endo_consts.inc"
 
 namespace zkcodec {
 
@@ -73,11 +74,40 @@ ZK_DEV bool on_curve(const Affine<F> &p) {
     if (p.is_inf()) return true;
     return p.y.sqr() == p.x.sqr() * p.x + curve_b((const F *)nullptr);
 }
+// r * P == infinity, literally as the reference does it (ec.rs:142-144); kept as the cross-check of the fast tests below
 template <class F>
-ZK_DEV bool in_subgroup(const Affine<F> &p) {   // r * P == infinity (ec.rs:142-144)
+ZK_DEV bool in_subgroup_by_order(const Affine<F> &p) {
     uint32_t r[8];
     for (int i = 0; i < 8; i++) r[i] = FrParams::mod(i);
     return scalar_mul(XYZZ<F>::from_affine(p), r).is_inf();
+}
+// The same predicate through the curve endomorphisms (Scott, eprint 2021/1130; El Housni-Guillevic-Piellard, eprint 2022/352,
+// which proves both tests exact for BLS12-381): with u = -0xd201000000010000,
+//   G1:  P in G1  <=>  phi(P) = -[u^2] P,  phi(x, y) = (beta x, y), beta a primitive cube root of unity      (127-bit multiple)
+//   G2:  Q in G2  <=>  psi(Q) = [u] Q,     psi = twist o Frobenius o untwist = (conj(x) cx, conj(y) cy)          (64-bit multiple)
+// instead of the 255-bit multiple by r: the verdict is identical, the cost 2.4x / 4x lower (constants: endo_consts.inc).
+ZK_DEV bool in_subgroup(const Affine<Fq> &p) {
+    if (p.is_inf()) return true;
+    const uint32_t beta_w[12] = ZK_ENDO_BETA_INIT;
+    const uint32_t k[8] = {0x00000000u, 0x00000001u, 0x0001a402u, 0xac45a401u, 0, 0, 0, 0};   // u^2 = 0xd201000000010000^2
+    XYZZ<Fq> t = scalar_mul(XYZZ<Fq>::from_affine(p), k);
+    if (t.is_inf()) return false;
+    Fq beta; for (int i = 0; i < 12; i++) beta.l[i] = beta_w[i];
+    return (p.x * beta) * t.zz == t.x && p.y * t.zzz == t.y.neg();
+}
+ZK_DEV bool in_subgroup(const Affine<Fq2> &p) {
+    if (p.is_inf()) return true;
+    const uint32_t c[2][24] = ZK_ENDO_PSI_INIT;
+    constexpr uint64_t U = 0xd201000000010000ull;
+    uint32_t k[8] = {(uint32_t)U, (uint32_t)(U >> 32), 0, 0, 0, 0, 0, 0};
+    XYZZ<Fq2> t = scalar_mul(XYZZ<Fq2>::from_affine(p), k);
+    if (t.is_inf()) return false;
+    Fq2 cx, cy;
+    for (int i = 0; i < 12; i++) { cx.c0.l[i] = c[0][i]; cx.c1.l[i] = c[0][12 + i]; cy.c0.l[i] = c[1][i]; cy.c1.l[i] = c[1][12 + i]; }
+    Fq2 px, py;
+    px.c0 = p.x.c0; px.c1 = p.x.c1.neg(); py.c0 = p.y.c0; py.c1 = p.y.c1.neg();
+    px = px * cx; py = py * cy;                       // psi(P), which must equal -[|u|] P
+    return px * t.zz == t.x && py * t.zzz == t.y.neg();
 }
 // into_affine / into_affine_unchecked of the Uncompressed encodings
 template <class F>

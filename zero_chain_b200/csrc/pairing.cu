@@ -327,11 +327,26 @@ extern "C" int zk_groth16_verify_batch_device(zk_ctx *ctx, const zk_pvk *k, size
     LineCoeff *coef = ctx->v_coef.as<LineCoeff>();
     Fq12 *f = ctx->v_f.as<Fq12>();
     XYZZ<Fq> *part = ctx->v_part.as<XYZZ<Fq>>();
+    // three independent strands, joined before the Miller loops: B decode + coefficients on the context's stream, A / C decode
+    // and the public-input sums on the two auxiliary lanes (a small batch is latency-bound, so the strands overlap fully)
+    if (!ctx->aux) ZK_TRY(zk_ctx_create(ctx->device, nullptr, &ctx->aux));
+    if (!ctx->aux2) ZK_TRY(zk_ctx_create(ctx->device, nullptr, &ctx->aux2));
+    cudaStream_t s2 = ctx->aux->stream, s3 = ctx->aux2->stream;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    ZK_CUDA(cudaEventCreateWithFlags(&ev0, cudaEventDisableTiming));
+    ZK_CUDA(cudaEventCreateWithFlags(&ev1, cudaEventDisableTiming));
+    ZK_CUDA(cudaEventCreateWithFlags(&ev2, cudaEventDisableTiming));
+    cudaEventRecord(ev0, st);
+    cudaStreamWaitEvent(s2, ev0, 0); cudaStreamWaitEvent(s3, ev0, 0);
+    k_proof_decode_g1<<<grid(2 * n), PT, 0, s2>>>(d_proofs, n, a, c, stt);
+    cudaEventRecord(ev1, s2);
+    if (n_inputs) k_ic_partial<<<grid(n * n_inputs), PT, 0, s3>>>(k->table, (const uint32_t *)d_inputs, n, n_inputs, part, ctx->d_err);
+    k_ic_sum<<<grid(n), PT, 0, s3>>>(part, k->ic, n, n_inputs, acc);
+    cudaEventRecord(ev2, s3);
     k_proof_decode_g2<<<grid(n), PT, 0, st>>>(d_proofs, n, b, stt);
-    k_proof_decode_g1<<<grid(2 * n), PT, 0, st>>>(d_proofs, n, a, c, stt);
-    if (n_inputs) k_ic_partial<<<grid(n * n_inputs), PT, 0, st>>>(k->table, (const uint32_t *)d_inputs, n, n_inputs, part, ctx->d_err);
-    k_ic_sum<<<grid(n), PT, 0, st>>>(part, k->ic, n, n_inputs, acc);
     k_g2_prepare<<<grid(n), PT, 0, st>>>(b, n, 0, coef, 1, n, stt + 1, 3);
+    cudaStreamWaitEvent(st, ev1, 0); cudaStreamWaitEvent(st, ev2, 0);
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2);     // released once the recorded work completes
     k_miller<<<grid(3 * n), PT, 0, st>>>(n, a, acc, c, coef, k->gamma, k->gamma_inf, k->delta, k->delta_inf, stt, f);
     k_verify_final<<<grid(n), PT, 0, st>>>(n, f, k->alpha_beta, stt, d_verdicts);
     ZK_CUDA(cudaGetLastError());
