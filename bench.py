@@ -32,8 +32,9 @@ sys.path.insert(0, ROOT)
 
 LOG_N = 20
 N_SETS = 8                     # distinct scalar vectors cycled through: 8 x 32 MiB = 256 MiB > 126 MB L2
-KERNELS_PER_MSM = 18           # digits, tile_hist, col_scan, 2 x (scan_block, scan_block, scan_add), scatter, pick_task_len,
-                               # accumulate, combine_serial, combine_warp, bit_sums, sum_points, finish_bits, encode
+KERNELS_PER_MSM = 24           # 20-bit windows at 2^20: digits, tile_hist, col_scan, 3 x scan_block, scan_add, scatter, fine_sort,
+                               # pick_task_len, len_hist, len_scan, len_place, accumulate, combine_serial, combine_warp,
+                               # rowcol_stage1, 2 x seg_sums, bit_sums, sum_points, finish_bits, join_rowcol, encode_xyzz
                                # (counted from the ncu launch list profiles/r01_launches_msm_2p20.csv; N > 1 adds the fold kernel)
 ALGO_MODMUL_PER_TERM = 176     # 11 (mixed add) x ceil(255/16) windows — the FIXED convention of SURVEY.md §8(d) / BASELINE.md §3,
                                # independent of the window size the library actually uses

@@ -194,3 +194,20 @@ def test_verify_full_batch_round_trip(ctx):
         inputs[i][i % 3] = (inputs[i][i % 3] + 1) % pr.R
     assert zk.verify_proofs(pvk, proofs, inputs) == [0 if i in flip else 1 for i in range(n)]
     pvk.free(); params.free()
+
+
+def test_verify_key_without_public_inputs(ctx):
+    """ic.len() == 1 (only the constant ONE): the public-input sum is ic[0] itself.  The key is the toy key with its ic cut
+    to one element, so no proof can be valid under it; what is checked is that the path agrees with the oracle."""
+    r1cs, crs, params = _setup(ctx, seed=17)
+    vkb = crs.params_bytes[:864] + (1).to_bytes(4, "big") + crs.params_bytes[868:868 + 96]
+    pvk = zk.PreparedVerifyingKey.prepare(ctx, vkb)
+    opvk = co.PreparedVerifyingKey.prepare(vkb)
+    assert pvk.num_inputs == 0 and pvk.write() == opvk.write()
+    z, proof = _prove(r1cs, params, 1, 3, 4)
+    got = zk.verify_proofs(pvk, proof * 2, [[], []])
+    assert got == opvk.verify_batch(proof * 2, np.zeros(0, np.uint64), 0) == [0, 0]
+    with pytest.raises(zk.SynthesisError) as e:
+        zk.verify_proofs(pvk, proof, [[1]])
+    assert e.value.code == -9
+    pvk.free(); params.free()

@@ -25,12 +25,12 @@ struct Fq2 {
     ZK_DEV Fq2 dbl() const { Fq2 r; r.c0 = c0.dbl(); r.c1 = c1.dbl(); return r; }
     ZK_DEV Fq2 neg() const { Fq2 r; r.c0 = c0.neg(); r.c1 = c1.neg(); return r; }
     ZK_DEV Fq2 cneg(bool f) const { return f ? neg() : *this; }
-    ZK_DEV friend Fq2 operator*(const Fq2 &a, const Fq2 &b) {   // (a0 b0 - a1 b1) + (a0 b1 + a1 b0) u
+    ZK_F2FN friend Fq2 operator*(const Fq2 &a, const Fq2 &b) {   // (a0 b0 - a1 b1) + (a0 b1 + a1 b0) u
         Fq aa = a.c0 * b.c0, bb = a.c1 * b.c1;
         Fq t = (a.c0 + a.c1) * (b.c0 + b.c1);
         Fq2 r; r.c1 = t - aa - bb; r.c0 = aa - bb; return r;
     }
-    ZK_DEV Fq2 sqr() const {   // (a0+a1)(a0-a1) + 2 a0 a1 u
+    ZK_F2FN Fq2 sqr() const {   // (a0+a1)(a0-a1) + 2 a0 a1 u
         Fq ab = c0 * c1;
         Fq2 r; r.c0 = (c0 + c1) * (c0 - c1); r.c1 = ab.dbl(); return r;
     }

@@ -27,9 +27,16 @@
 #define ZK_DEV inline
 #define ZK_MULFN inline
 #define ZK_PTFN inline
+#define ZK_F2FN inline
 #elif defined(ZK_HOT)
 #define ZK_MULFN __device__ __forceinline__
 #define ZK_PTFN __device__ __forceinline__
+#elif defined(ZK_SEMI_HOT)
+// pairing.cu: the Fq product is inlined into its callers, and the Fq2 product / square become the call boundary, so the
+// three (two) independent Montgomery chains of one Fq2 operation interleave in the integer pipe
+#define ZK_MULFN __device__ __forceinline__
+#define ZK_PTFN __device__ __noinline__
+#define ZK_F2FN __device__ __noinline__
 #else
 #define ZK_MULFN __device__ __noinline__
 #define ZK_PTFN __device__ __noinline__
@@ -53,6 +60,9 @@ inline uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return mul_hi(a, b
 }  // namespace zkprim
 #else
 #define ZK_DEV __device__ __forceinline__
+#ifndef ZK_F2FN
+#define ZK_F2FN ZK_DEV
+#endif
 namespace zkprim {
 // The PTX condition-code register carries between consecutive asm volatile statements (the
 // established CGBN / sppark idiom): volatile asms are not reordered against each other.

@@ -13,6 +13,7 @@
 // HBM layout: per-proof arrays are structure-of-items ([item][fields]); the B_i coefficients are stored [k][i] so that
 // the threads of a warp read neighbouring 288-byte records at every step of the loop; -gamma / -delta coefficients are
 // one shared array (broadcast reads through L1/L2).  All of it is Fq multiply-bound (int32 pipe), not HBM-bound.
+#define ZK_SEMI_HOT 1
 #include "internal.h"
 #include "codec.cuh"
 #include "pairing.cuh"
