@@ -127,15 +127,36 @@ __global__ void k_put_terms(const uint4 *__restrict__ terms, int sel0, int sel1,
         d[0] = s[0]; d[1] = s[1];
     }
 }
-// thread per (proof, j): T[b][j] = (j == 0 ? s : r) * (j == 0 ? g_a : g_b1)
-__global__ void __launch_bounds__(64) k_scale_points(const G1XYZZ *__restrict__ ga, const G1XYZZ *__restrict__ gb1, const uint32_t *__restrict__ terms,
-                                                     size_t batch, G1XYZZ *__restrict__ T) {
-    size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= 2 * batch) return;
-    size_t b = id >> 1; int j = id & 1;
-    uint32_t k[8];
-    for (int i = 0; i < 8; i++) k[i] = terms[(b * 4 + (j ? 1 : 2)) * 8 + i];     // j=0: s, j=1: r
-    T[id] = scalar_mul(j ? gb1[b] : ga[b], k);
+// block per (proof, j): T[b][j] = (j == 0 ? s : r) * (j == 0 ? g_a : g_b1).  A 255-bit double-and-add on one thread is ~380
+// dependent point operations; here thread 0 runs the doubling chain 2^i P into shared memory (the only serial part) and the
+// block then sums the selected powers: 4 per thread, then a 6-level tree — about 2.5x less latency for the same group element.
+constexpr int SCALE_T = 64;
+__global__ void __launch_bounds__(SCALE_T) k_scale_points(const G1XYZZ *__restrict__ ga, const G1XYZZ *__restrict__ gb1, const uint32_t *__restrict__ terms,
+                                                          size_t batch, G1XYZZ *__restrict__ T) {
+    __shared__ G1XYZZ pw[255];                                                   // 2^i P, i <= 254; reused for the tree (47.8 KB)
+    const size_t id = blockIdx.x;
+    const size_t b = id >> 1; const int j = (int)(id & 1), t = threadIdx.x;
+    const uint32_t *k = terms + (b * 4 + (j ? 1 : 2)) * 8;                       // j=0: s, j=1: r
+    int top = -1;
+    for (int i = 7; i >= 0 && top < 0; i--) if (k[i]) top = 32 * i + 31 - __clz(k[i]);
+    if (t == 0) {
+        G1XYZZ d = j ? gb1[b] : ga[b];
+        pw[0] = d;
+        for (int i = 1; i <= top; i++) { d = d.dbl(); pw[i] = d; }
+    }
+    __syncthreads();
+    G1XYZZ acc = G1XYZZ::inf();
+    for (int i = 4 * t; i < 4 * t + 4 && i <= top; i++)
+        if ((k[i >> 5] >> (i & 31)) & 1) acc.add(pw[i]);
+    __syncthreads();                                                             // every thread is done reading the powers
+    G1XYZZ *part = pw;
+    part[t] = acc;
+    __syncthreads();
+    for (int stride = SCALE_T / 2; stride > 0; stride >>= 1) {
+        if (t < stride) { G1XYZZ a = part[t]; a.add(part[t + stride]); part[t] = a; }
+        __syncthreads();
+    }
+    if (t == 0) T[id] = part[0];
 }
 // thread per proof: g_c = T0 + T1 + H' + L; write Proof (compressed a | b | c)
 __global__ void __launch_bounds__(64) k_finish_proofs(const G1XYZZ *__restrict__ ga, const G2XYZZ *__restrict__ gb, const G1XYZZ *__restrict__ T,
@@ -255,6 +276,8 @@ static int prove_impl(zk_ctx *ctx, const zk_params *p, size_t batch,
     }
     if (rc3 == ZK_OK) {
         cudaMemcpyAsync(d_gb1, lane3->result.p, batch * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, lane3->stream);
+        // s*g_a and r*g_b1 need only this lane's results, so they run here, under the NTT -> H -> L chain of the first lane
+        k_scale_points<<<(unsigned)(2 * batch), SCALE_T, 0, lane3->stream>>>(d_ga, d_gb1, (const uint32_t *)d_terms, batch, d_T);
         cudaEventRecord(ev_l3, lane3->stream);
     } else { cudaEventDestroy(ev_b); cudaEventDestroy(ev_g2); cudaEventDestroy(ev_a); cudaEventDestroy(ev_l3); return rc3; }
     if (r1cs) {
@@ -283,10 +306,9 @@ static int prove_impl(zk_ctx *ctx, const zk_params *p, size_t batch,
     // L
     ZK_TRY(zk_msm_run(ctx, p->l, d_aux, n_aux, batch));
     ZK_CUDA(cudaMemcpyAsync(d_L, ctx->result.p, batch * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, st));
-    ZK_CUDA(cudaStreamWaitEvent(st, ev_l3, 0));                       // join: g_a, g_b1 from the third lane
+    ZK_CUDA(cudaStreamWaitEvent(st, ev_l3, 0));                       // join: g_a, g_b1 and the scaled points T from the third lane
     ZK_CUDA(cudaStreamWaitEvent(st, ev_g2, 0));                       // join: g_b (G2) is ready in d_gb
     // ---- assembly + Proof::write ----
-    k_scale_points<<<(unsigned)((2 * batch + 63) / 64), 64, 0, st>>>(d_ga, d_gb1, (const uint32_t *)d_terms, batch, d_T);
     k_finish_proofs<<<(unsigned)((batch + 63) / 64), 64, 0, st>>>(d_ga, d_gb, d_T, d_H, d_L, batch, d_proofs);
     ZK_CUDA(cudaGetLastError());
     ZK_CUDA(cudaMemcpyAsync(proofs_out, d_proofs, batch * 192, cudaMemcpyDeviceToHost, st));
