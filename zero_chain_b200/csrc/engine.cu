@@ -1,6 +1,9 @@
 // libzkb200: execution context, MSM driver and diagnostics (host side of the C ABI, include/zkb200.h).
 // The reference's counterpart is bellman's `multiexp` + `Worker` CPU pool (un-vendored);
 // here the "pool" is one CUDA stream per context and the schedule documented in msm.cuh.
+// Built "semi-hot" (field.cuh): the Fq product is inlined, the Fq2 product / square is the call boundary — the G2 MSM kernels of this
+// translation unit run 10-20 % faster than with the Fq product as a function call, at 36 s of compile time.
+#define ZK_SEMI_HOT 1
 #include "internal.h"
 #include "msm_driver.cuh"
 

@@ -14,6 +14,7 @@
 //   g_c = s*g_a + r*g_b1 + (H - rs*delta_g1) + L
 // which equals bellman's  delta*rs + alpha*s + beta*r + A*s + B1*r + H + L.  A whole batch of proofs
 // shares every launch: NTTs are batched (grid.y) and each MSM uses one window set per proof.
+#define ZK_SEMI_HOT 1   // Fq product inlined into the (noinline) point operations: shorter dependent chains in k_scale_points / k_finish_proofs
 #include "internal.h"
 #include "codec.cuh"
 

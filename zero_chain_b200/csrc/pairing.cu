@@ -221,7 +221,7 @@ extern "C" int zk_pvk_load(zk_ctx *ctx, const uint8_t *buf, size_t len, zk_pvk *
     if (r) { zk_pvk_free(k); return r; }
     uint8_t *d = ctx->stage_a.as<uint8_t>();
     int *err = ctx->d_err + 1;
-    cudaMemcpyAsync(d, buf, total, cudaMemcpyHostToDevice, ctx->stream);
+    if (cudaMemcpyAsync(d, buf, total, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { zk_pvk_free(k); zk_set_error("zk_pvk_load: copy failed"); return ZK_ERR_CUDA; }
     k_fq_load_be<<<1, 32, 0, ctx->stream>>>(d, 12, (Fq *)k->alpha_beta, err);
     for (int g = 0; g < 2; g++) {
         LineCoeff *dst = g ? k->delta : k->gamma;
@@ -267,7 +267,7 @@ extern "C" int zk_pvk_prepare(zk_ctx *ctx, const uint8_t *vk, size_t len, zk_pvk
     G1A *g1 = ctx->stage_b.as<G1A>();                       // [0] alpha, [1] delta_g1 (validated only)
     G2A *g2 = (G2A *)(g1 + 2);                              // [0] beta, [1] gamma, [2] delta
     int *err = ctx->d_err + 1;
-    cudaMemcpyAsync(d, vk, total, cudaMemcpyHostToDevice, ctx->stream);
+    if (cudaMemcpyAsync(d, vk, total, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { zk_pvk_free(k); zk_set_error("zk_pvk_prepare: copy failed"); return ZK_ERR_CUDA; }
     zkcodec::k_decode_uncompressed<Fq><<<1, 128, 0, ctx->stream>>>(d, 2, 1, 1, g1, err);                 // alpha_g1, beta_g1 (overwritten next)
     zkcodec::k_decode_uncompressed<Fq><<<1, 128, 0, ctx->stream>>>(d + 576, 1, 1, 1, g1 + 1, err);       // delta_g1
     zkcodec::k_decode_uncompressed<Fq2><<<1, 128, 0, ctx->stream>>>(d + 192, 2, 1, 1, g2, err);          // beta_g2, gamma_g2
@@ -333,21 +333,21 @@ extern "C" int zk_groth16_verify_batch_device(zk_ctx *ctx, const zk_pvk *k, size
     if (!ctx->aux) ZK_TRY(zk_ctx_create(ctx->device, nullptr, &ctx->aux));
     if (!ctx->aux2) ZK_TRY(zk_ctx_create(ctx->device, nullptr, &ctx->aux2));
     cudaStream_t s2 = ctx->aux->stream, s3 = ctx->aux2->stream;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
-    ZK_CUDA(cudaEventCreateWithFlags(&ev0, cudaEventDisableTiming));
-    ZK_CUDA(cudaEventCreateWithFlags(&ev1, cudaEventDisableTiming));
-    ZK_CUDA(cudaEventCreateWithFlags(&ev2, cudaEventDisableTiming));
-    cudaEventRecord(ev0, st);
-    cudaStreamWaitEvent(s2, ev0, 0); cudaStreamWaitEvent(s3, ev0, 0);
+    struct Events {                                                       // destroyed on every exit path
+        cudaEvent_t e[3] = {nullptr, nullptr, nullptr};
+        ~Events() { for (cudaEvent_t x : e) if (x) cudaEventDestroy(x); }     // a recorded event is released once its work completes
+    } ev;
+    for (cudaEvent_t &x : ev.e) ZK_CUDA(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
+    ZK_CUDA(cudaEventRecord(ev.e[0], st));
+    ZK_CUDA(cudaStreamWaitEvent(s2, ev.e[0], 0)); ZK_CUDA(cudaStreamWaitEvent(s3, ev.e[0], 0));
     k_proof_decode_g1<<<grid(2 * n), PT, 0, s2>>>(d_proofs, n, a, c, stt);
-    cudaEventRecord(ev1, s2);
+    ZK_CUDA(cudaEventRecord(ev.e[1], s2));
     if (n_inputs) k_ic_partial<<<grid(n * n_inputs), PT, 0, s3>>>(k->table, (const uint32_t *)d_inputs, n, n_inputs, part, ctx->d_err);
     k_ic_sum<<<grid(n), PT, 0, s3>>>(part, k->ic, n, n_inputs, acc);
-    cudaEventRecord(ev2, s3);
+    ZK_CUDA(cudaEventRecord(ev.e[2], s3));
     k_proof_decode_g2<<<grid(n), PT, 0, st>>>(d_proofs, n, b, stt);
     k_g2_prepare<<<grid(n), PT, 0, st>>>(b, n, 0, coef, 1, n, stt + 1, 3);
-    cudaStreamWaitEvent(st, ev1, 0); cudaStreamWaitEvent(st, ev2, 0);
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2);     // released once the recorded work completes
+    ZK_CUDA(cudaStreamWaitEvent(st, ev.e[1], 0)); ZK_CUDA(cudaStreamWaitEvent(st, ev.e[2], 0));
     k_miller<<<grid(3 * n), PT, 0, st>>>(n, a, acc, c, coef, k->gamma, k->gamma_inf, k->delta, k->delta_inf, stt, f);
     k_verify_final<<<grid(n), PT, 0, st>>>(n, f, k->alpha_beta, stt, d_verdicts);
     ZK_CUDA(cudaGetLastError());
