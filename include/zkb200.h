@@ -72,6 +72,14 @@ int zk_bases_window_bits(const zk_bases *b);
 int zk_msm(zk_ctx *ctx, const zk_bases *b, const uint64_t *scalars, size_t n, uint8_t *out);
 /* same with scalars already resident in DEVICE memory (kernel-only timing; prover-internal use) */
 int zk_msm_device(zk_ctx *ctx, const zk_bases *b, const void *d_scalars, size_t n, uint8_t *out);
+/* The same MSM as a future, which is what bellman's multiexp returns (multiexp.rs: Box<Future<Item = G>>): begin enqueues the
+ * upload (host variant), the MSM, the affine conversion and the download of the encoded point, and returns; end waits and
+ * hands out the 96 / 192 bytes.  One MSM may be in flight per context.  Everything after the bucket accumulation runs on a
+ * high-priority stream of the context, so two contexts used alternately overlap the latency-bound tail of one MSM (and the
+ * upload of the next scalars) with the accumulation of the other — results are identical to zk_msm / zk_msm_device. */
+int zk_msm_begin(zk_ctx *ctx, const zk_bases *b, const uint64_t *scalars, size_t n);
+int zk_msm_device_begin(zk_ctx *ctx, const zk_bases *b, const void *d_scalars, size_t n);
+int zk_msm_end(zk_ctx *ctx, uint8_t *out);
 /* batch of `batch` independent scalar vectors (each n long, contiguous) against the same bases;
  * out: batch encodings.  Used by the batched prover. */
 int zk_msm_batch_device(zk_ctx *ctx, const zk_bases *b, const void *d_scalars, size_t n, size_t batch, uint8_t *out);

@@ -221,3 +221,37 @@ def test_msm_g2_batch_and_adhoc(ctx):
     b = zk.Bases(ctx, 2, bases, window_bits=7, precompute=False)    # ad-hoc path: one bucket set per window + Horner
     assert zk.multiexp(b, scal[0]) == _enc(2, co.g2_msm(bases, scal[0]))
     b.free()
+
+
+def test_multiexp_future_matches_blocking_call():
+    """zk_msm_begin / zk_msm_end (bellman's multiexp returns a future): same bytes as the blocking call, one MSM in flight
+    per context, two contexts pipelined over shared bases."""
+    import torch
+    c1, c2 = zk.Context(0), zk.Context(0)
+    n = 1 << 14
+    bases = zk.scalar_mul_many(c1, 1, zk.G1_GENERATOR, sy.random_fr_limbs(n, 31))
+    b = zk.Bases(c1, 1, bases)
+    sets = [sy.random_fr_limbs(n, 40 + k) for k in range(5)]
+    want = [zk.multiexp(b, s) for s in sets]
+    assert want[0] == co.g1_encode(co.g1_msm(bases, sets[0]), False)
+    # host-scalar futures, alternating contexts, two in flight
+    ctxs = [c1, c2]
+    got = [None] * len(sets)
+    for k, s in enumerate(sets):
+        c = ctxs[k % 2]
+        if k >= 2:
+            got[k - 2] = zk.multiexp_end(c, b)
+        zk.multiexp_begin(c, b, s)
+    for k in range(len(sets) - 2, len(sets)):
+        got[k] = zk.multiexp_end(ctxs[k % 2], b)
+    assert got == want
+    # device-scalar future
+    d = torch.from_numpy(sets[1].view(np.int64)).cuda()
+    zk.multiexp_device_begin(c2, b, d.data_ptr(), n)
+    with pytest.raises(zk.ZkError):
+        zk.multiexp_device_begin(c2, b, d.data_ptr(), n)           # one in flight per context
+    assert zk.multiexp_end(c2, b) == want[1]
+    with pytest.raises(zk.ZkError):
+        zk.multiexp_end(c2, b)                                      # nothing in flight
+    assert zk.multiexp(b, sets[2]) == want[2]                       # the blocking call still works on the same context
+    b.free(); c2.close(); c1.close()

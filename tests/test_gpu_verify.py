@@ -192,7 +192,13 @@ def test_verify_full_batch_round_trip(ctx):
     flip = set(range(0, n, 7))
     for i in flip:
         inputs[i][i % 3] = (inputs[i][i % 3] + 1) % pr.R
-    assert zk.verify_proofs(pvk, proofs, inputs) == [0 if i in flip else 1 for i in range(n)]
+    want = [0 if i in flip else 1 for i in range(n)]
+    assert zk.verify_proofs(pvk, proofs, inputs) == want
+    os.environ["ZK_VERIFY_CHUNK"] = "100"            # the slicing path of very large batches (default slice: 2^18 proofs)
+    try:
+        assert zk.verify_proofs(pvk, proofs, inputs) == want
+    finally:
+        del os.environ["ZK_VERIFY_CHUNK"]
     pvk.free(); params.free()
 
 

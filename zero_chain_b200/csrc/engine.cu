@@ -54,6 +54,7 @@ extern "C" void zk_ctx_destroy(zk_ctx *c) {
                       &c->aff_pts0, &c->aff_pts1, &c->aff_scratch, &c->aff_off0, &c->aff_off1, &c->aff_sizes0, &c->aff_sizes1, &c->red_rows, &c->g_scal2, &c->g_scal3, &c->sorted2, &c->coarse_off, &c->coarse_sizes, &c->task_order, &c->len_hist, &c->heavy_list, &c->red_tmp,
                       &c->v_pts, &c->v_stat, &c->v_coef, &c->v_f, &c->v_part, &c->v_io};
     for (DevBuf *b : bufs) b->release();
+    if (c->tail) { cudaStreamSynchronize(c->tail); cudaStreamDestroy(c->tail); cudaEventDestroy(c->ev_front); cudaEventDestroy(c->ev_tail); }
     if (c->d_err) cudaFree(c->d_err);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -178,6 +179,57 @@ extern "C" int zk_msm(zk_ctx *ctx, const zk_bases *b, const uint64_t *scalars, s
     ZK_TRY(ctx->scalars.reserve(n * 32));
     ZK_CUDA(cudaMemcpyAsync(ctx->scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
     return zk_msm_device(ctx, b, ctx->scalars.p, n, out);
+}
+// ---- asynchronous MSM: bellman's multiexp returns a future (multiexp.rs); begin / end is that future on CUDA streams ----
+static int msm_begin_common(zk_ctx *ctx, const zk_bases *b, const void *d_scalars, size_t n) {
+    if (!ctx->tail) {
+        int lo = 0, hi = 0;
+        ZK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        ZK_CUDA(cudaStreamCreateWithPriority(&ctx->tail, cudaStreamNonBlocking, hi));
+        ZK_CUDA(cudaEventCreateWithFlags(&ctx->ev_front, cudaEventDisableTiming));
+        ZK_CUDA(cudaEventCreateWithFlags(&ctx->ev_tail, cudaEventDisableTiming));
+    }
+    const size_t per = b->group == 1 ? 96 : 192;
+    ZK_TRY(ctx->out_bytes.reserve(per));
+    ctx->split_tail = true;
+    int r = zk_msm_run(ctx, b, d_scalars, n, 1);
+    ctx->split_tail = false;
+    if (r) return r;
+    cudaStream_t saved = ctx->stream;
+    ctx->stream = ctx->tail;                    // affine conversion + wire format + D2H stay on the tail stream
+    r = b->group == 1 ? zk_encode_results_g1(ctx, 1, 0, ctx->out_bytes.as<uint8_t>()) : encode_results_t<Fq2>(ctx, 1, 0, ctx->out_bytes.as<uint8_t>());
+    ctx->stream = saved;
+    if (r) return r;
+    ZK_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->out_bytes.p, per, cudaMemcpyDeviceToHost, ctx->tail));
+    ZK_CUDA(cudaEventRecord(ctx->ev_tail, ctx->tail));
+    ZK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_tail, 0));       // later work on the context's stream stays ordered after this MSM
+    ctx->pending_bytes = per;
+    return ZK_OK;
+}
+extern "C" int zk_msm_device_begin(zk_ctx *ctx, const zk_bases *b, const void *d_scalars, size_t n) {
+    if (!ctx || !b || !d_scalars) { zk_set_error("zk_msm_device_begin: NULL argument"); return ZK_ERR_INVALID; }
+    if (ctx->pending_bytes) { zk_set_error("zk_msm_device_begin: an MSM is already in flight on this context (call zk_msm_end first)"); return ZK_ERR_INVALID; }
+    ZK_TRY(zk_use_device(ctx));
+    return msm_begin_common(ctx, b, d_scalars, n);
+}
+extern "C" int zk_msm_begin(zk_ctx *ctx, const zk_bases *b, const uint64_t *scalars, size_t n) {
+    if (!ctx || !b || !scalars) { zk_set_error("zk_msm_begin: NULL argument"); return ZK_ERR_INVALID; }
+    if (ctx->pending_bytes) { zk_set_error("zk_msm_begin: an MSM is already in flight on this context (call zk_msm_end first)"); return ZK_ERR_INVALID; }
+    ZK_TRY(zk_use_device(ctx));
+    ZK_TRY(ctx->scalars.reserve(n * 32));
+    ZK_CUDA(cudaMemcpyAsync(ctx->scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    return msm_begin_common(ctx, b, ctx->scalars.p, n);
+}
+extern "C" int zk_msm_end(zk_ctx *ctx, uint8_t *out) {
+    if (!ctx || !out) { zk_set_error("zk_msm_end: NULL argument"); return ZK_ERR_INVALID; }
+    if (!ctx->pending_bytes) { zk_set_error("zk_msm_end: no MSM in flight"); return ZK_ERR_INVALID; }
+    ZK_TRY(zk_use_device(ctx));
+    size_t per = ctx->pending_bytes;
+    ctx->pending_bytes = 0;
+    ZK_CUDA(cudaEventSynchronize(ctx->ev_tail));
+    ZK_TRY(zk_check_err_flag(ctx));
+    memcpy(out, ctx->h_pinned, per);
+    return ZK_OK;
 }
 extern "C" size_t zk_partial_size(int group) { return group == 1 ? sizeof(G1XYZZ) : sizeof(G2XYZZ); }
 extern "C" int zk_msm_partial_device(zk_ctx *ctx, const zk_bases *b, const void *d_scalars, size_t n, void *d_partial_out) {

@@ -63,6 +63,12 @@ struct zk_ctx {
     DevBuf g_scal3;                // A-query scalars
     zk_ctx *aux = nullptr;         // second lane (own stream + workspace) on the same device: the prover's G2 MSM overlaps the G1 work
     DevBuf g_scal2;                // B-query scalars (shared by the G1 and G2 B MSMs)
+    // asynchronous MSM (zk_msm_begin / zk_msm_end): everything after the bucket accumulation runs on a HIGH-PRIORITY stream, so that
+    // with two contexts in flight the latency-bound tail of one MSM is scheduled ahead of the other's accumulation blocks
+    cudaStream_t tail = nullptr;
+    cudaEvent_t ev_front = nullptr, ev_tail = nullptr;
+    bool split_tail = false;       // set by zk_msm_*begin around the driver call
+    size_t pending_bytes = 0;      // result bytes of the MSM in flight (0 = none)
     uint8_t *h_pinned = nullptr;   // small pinned buffer for results
     size_t h_pinned_cap = 0;
 };

@@ -154,6 +154,11 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
         else k_accumulate<F, 2><<<grid, 128, 0, st>>>(tb, so, bo, to, (uint32_t)NB, order, partials);
     }
     if (ctx->prof_on) { cudaEventRecord(ev1, st); ctx->prof_events.push_back(ev0); ctx->prof_events.push_back(ev1); }
+    if (ctx->split_tail) {             // asynchronous MSM: combine / reduction continue on the high-priority tail stream
+        ZK_CUDA(cudaEventRecord(ctx->ev_front, st));
+        ZK_CUDA(cudaStreamWaitEvent(ctx->tail, ctx->ev_front, 0));
+        st = ctx->tail;
+    }
     const size_t sm_warp = 4 * 32 * pt;      // 4 warps x 32 points
     if (sm_warp > 48 * 1024) {
         ZK_CUDA(cudaFuncSetAttribute(k_combine_warp<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_warp));

@@ -14,6 +14,7 @@
 // the threads of a warp read neighbouring 288-byte records at every step of the loop; -gamma / -delta coefficients are
 // one shared array (broadcast reads through L1/L2).  All of it is Fq multiply-bound (int32 pipe), not HBM-bound.
 #define ZK_SEMI_HOT 1
+#include <stdlib.h>
 #include "internal.h"
 #include "codec.cuh"
 #include "pairing.cuh"
@@ -161,6 +162,7 @@ static unsigned grid(size_t n, int t = PT) { return (unsigned)((n + t - 1) / t);
 static uint32_t rd_u32be(const uint8_t *p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
 static void wr_u32be(uint8_t *p, uint32_t v) { p[0] = (uint8_t)(v >> 24); p[1] = (uint8_t)(v >> 16); p[2] = (uint8_t)(v >> 8); p[3] = (uint8_t)v; }
 constexpr size_t COEF_BYTES = (size_t)N_COEFFS * 288;
+constexpr size_t VERIFY_CHUNK = (size_t)1 << 18;      // proofs per slice of zk_groth16_verify_batch (5 GB of workspace)
 
 extern "C" void zk_pvk_free(zk_pvk *k) {
     if (!k) return;
@@ -316,6 +318,15 @@ extern "C" int zk_groth16_verify_batch_device(zk_ctx *ctx, const zk_pvk *k, size
     if (!n) return ZK_OK;
     ZK_TRY(zk_use_device(ctx));
     if (k->device != ctx->device) { zk_set_error("prepared key lives on device %d, context on %d", k->device, ctx->device); return ZK_ERR_INVALID; }
+    size_t chunk = VERIFY_CHUNK;
+    if (const char *e = getenv("ZK_VERIFY_CHUNK")) { long v = atol(e); if (v > 0) chunk = (size_t)v; }     // test hook
+    if (n > chunk) {                   // bound the workspace (19.6 KB of B coefficients per proof): slices run back to back on the stream
+        for (size_t o = 0; o < n; o += chunk) {
+            size_t m = n - o < chunk ? n - o : chunk;
+            ZK_TRY(zk_groth16_verify_batch_device(ctx, k, m, d_proofs + 192 * o, d_inputs + 4 * n_inputs * o, n_inputs, d_verdicts + o));
+        }
+        return ZK_OK;
+    }
     cudaStream_t st = ctx->stream;
     ZK_TRY(ctx->v_pts.reserve(n * (3 * sizeof(G1A) + sizeof(G2A))));
     ZK_TRY(ctx->v_stat.reserve(3 * n));

@@ -121,6 +121,25 @@ def multiexp(bases: Bases, exponents) -> bytes:
     return out.tobytes()
 
 
+def multiexp_begin(ctx: Context, bases: Bases, exponents):
+    """multiexp as a future (bellman's multiexp returns one): enqueue on `ctx`, collect with multiexp_end(ctx, bases).  `bases`
+    may have been created through another context of the same device; alternate two contexts to pipeline successive MSMs."""
+    e = _u64(exponents, (-1, 4))
+    _ck(_lib.lib().zk_msm_begin(ctx._h, bases._h, _p(e), e.shape[0]))
+    ctx._keep = e                         # the upload is asynchronous: keep the buffer alive until multiexp_end
+
+
+def multiexp_device_begin(ctx: Context, bases: Bases, d_scalars_ptr: int, n: int):
+    _ck(_lib.lib().zk_msm_device_begin(ctx._h, bases._h, C.c_void_p(d_scalars_ptr), n))
+
+
+def multiexp_end(ctx: Context, bases: Bases) -> bytes:
+    out = np.zeros(96 if bases.group == 1 else 192, np.uint8)
+    _ck(_lib.lib().zk_msm_end(ctx._h, _p(out)))
+    ctx._keep = None
+    return out.tobytes()
+
+
 def multiexp_partial_device(bases: Bases, d_scalars_ptr: int, n: int, d_out_ptr: int):
     """Partial MSM result (XYZZ point, zk_partial_size bytes) left in device memory for the NCCL all-gather."""
     _ck(_lib.lib().zk_msm_partial_device(bases.ctx._h, bases._h, C.c_void_p(d_scalars_ptr), n, C.c_void_p(d_out_ptr)))
