@@ -123,7 +123,9 @@ def run_ours(args):
         saved = os.dup(1)
         os.dup2(2, 1)
         try:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.is_high_priority_stream = True          # the 192-byte all-gather belongs to the latency-bound tail of an MSM
+            dist.init_process_group("nccl", pg_options=opts, device_id=torch.device("cuda", local))
             warm = torch.zeros(1, device="cuda")
             dist.all_reduce(warm)
             torch.cuda.synchronize()
@@ -201,7 +203,7 @@ def run_ours(args):
     # world == 1: successive MSMs are independent jobs, and the reference's multiexp returns a future — the timed loop keeps two
     # of them in flight on two contexts (zk_msm_begin / zk_msm_end), so the latency-bound tail of one MSM and the upload of the
     # next scalars overlap the accumulation of the other.  The blocking single-call numbers are reported beside it.
-    ctx2 = zk.Context(local) if world == 1 else None
+    ctx2 = zk.Context(local)
 
     def timed_pipelined(begin, steps, warmup, profile=False):
         ctxs = [ctx, ctx2]
@@ -227,6 +229,10 @@ def run_ours(args):
         e1.record(stream)                      # every MSM has been collected on the host, so this is after all of the work
         barrier()
         ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
         prof = None
         if profile:
             a, b_ = ctx.profile_read(), ctx2.profile_read()
@@ -234,30 +240,47 @@ def run_ours(args):
             ctx.profile(False); ctx2.profile(False)
         return ms, res[warmup + steps - 1], prof
 
-    begin_device = lambda c, k: zk.multiexp_device_begin(c, bases, d_sets[k % N_SETS].data_ptr(), n)
-    begin_e2e = lambda c, k: zk.multiexp_begin(c, bases, pinned[k % N_SETS].numpy().view(np.uint64).reshape(-1, 4))
+    if world == 1:
+        begin_device = lambda c, k: zk.multiexp_device_begin(c, bases, d_sets[k % N_SETS].data_ptr(), n)
+        begin_e2e = lambda c, k: zk.multiexp_begin(c, bases, pinned[k % N_SETS].numpy().view(np.uint64).reshape(-1, 4))
+    else:
+        # per context: its partial, the gathered partials, a staging buffer for the e2e arm, and torch views of its two streams
+        lanes = {}
+        for c in (ctx, ctx2):
+            lanes[id(c)] = dict(part=torch.zeros(psz, dtype=torch.uint8, device="cuda"), all=torch.zeros(psz * world, dtype=torch.uint8, device="cuda"),
+                                stage=torch.empty_like(d_sets[0]), main=torch.cuda.ExternalStream(c.stream, device=torch.device("cuda", local)),
+                                tail=torch.cuda.ExternalStream(zk.tail_stream(c), device=torch.device("cuda", local)))
+
+        def begin_multi(c, d_ptr):
+            L = lanes[id(c)]
+            zk.multiexp_partial_device_begin(c, bases, d_ptr, n, L["part"].data_ptr())
+            with torch.cuda.stream(L["tail"]):          # the all-gather is ordered after the partial on the context's tail stream
+                dist.all_gather_into_tensor(L["all"], L["part"])
+            zk.points_fold_begin(c, 1, L["all"].data_ptr(), world)
+
+        begin_device = lambda c, k: begin_multi(c, d_sets[k % N_SETS].data_ptr())
+
+        def begin_e2e(c, k):
+            L = lanes[id(c)]
+            with torch.cuda.stream(L["main"]):
+                L["stage"].copy_(pinned[k % N_SETS], non_blocking=True)
+            begin_multi(c, L["stage"].data_ptr())
 
     # modmul roofline calibrated live on this GPU (register-resident independent Fq products)
     modmul_peak, _ = zk.bench_modmul(ctx, zk.FIELD_FQ, 148 * 4, 256, 3000)
 
     sampler = ClockSampler(local) if rank == 0 else None
-    blocking = None
-    W = max(4, args.warmup) if world == 1 else args.warmup      # the last timed step (W + steps - 1) picks the scalar set the CPU check uses
-    if world == 1:
-        ms_dev, res_dev, prof = timed_pipelined(begin_device, args.steps, W, profile=True)
-        clocks = sampler.stop() if sampler else None
-        ms_e2e, res_e2e, _ = timed_pipelined(begin_e2e, args.steps, W)
-        ms_b, res_b, _ = timed(step_device, args.steps, W)
-        ms_be, res_be, _ = timed(step_e2e, args.steps, W)
-        if not (res_b == res_dev and res_be == res_e2e):
-            raise SystemExit("PARITY FAILURE: pipelined and blocking MSM results differ")
-        blocking = {"device_ms_per_step": ms_b / args.steps, "device_mops": n * args.steps / (ms_b * 1e-3) / 1e6,
-                    "e2e_ms_per_step": ms_be / args.steps, "e2e_mops": n * args.steps / (ms_be * 1e-3) / 1e6,
-                    "api": "zk_msm_device / zk_msm, one call at a time (latency of a single MSM)"}
-    else:
-        ms_dev, res_dev, prof = timed(step_device, args.steps, W, profile=True)
-        clocks = sampler.stop() if sampler else None
-        ms_e2e, res_e2e, _ = timed(step_e2e, args.steps, W)
+    W = max(4, args.warmup)            # the last timed step (W + steps - 1) picks the scalar set the CPU check uses
+    ms_dev, res_dev, prof = timed_pipelined(begin_device, args.steps, W, profile=True)
+    clocks = sampler.stop() if sampler else None
+    ms_e2e, res_e2e, _ = timed_pipelined(begin_e2e, args.steps, W)
+    ms_b, res_b, _ = timed(step_device, args.steps, W)
+    ms_be, res_be, _ = timed(step_e2e, args.steps, W)
+    if not (res_b == res_dev and res_be == res_e2e):
+        raise SystemExit("PARITY FAILURE: pipelined and blocking MSM results differ")
+    blocking = {"device_ms_per_step": ms_b / args.steps, "device_mops": n * world * args.steps / (ms_b * 1e-3) / 1e6,
+                "e2e_ms_per_step": ms_be / args.steps, "e2e_mops": n * world * args.steps / (ms_be * 1e-3) / 1e6,
+                "api": "zk_msm_device / zk_msm (N > 1: zk_msm_partial_device + all-gather + zk_points_fold), one call at a time"}
 
     total_terms = n * world
     value = total_terms * args.steps / (ms_dev * 1e-3) / 1e6
@@ -327,7 +350,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "Mop/s", "h2d_bytes_per_step": n * 32 * world, "d2h_bytes_per_step": 96 * world,
                     "ms_per_step": ms_e2e / args.steps,
                     "api": "zk_msm_begin / zk_msm_end (C ABI futures, scalars in pinned host memory, two in flight)" if world == 1 else
-                           "zk_msm_partial_device after an H2D copy of the scalars + NCCL all-gather + zk_points_fold"},
+                           "H2D copy of the scalars + zk_msm_partial_device_begin + NCCL all-gather + zk_points_fold_begin / zk_msm_end, two in flight"},
             "gpu_launches": (KERNELS_PER_MSM + (1 if world > 1 else 0)) * args.steps * world,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
         }
@@ -344,12 +367,13 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     # ordered teardown: tensors that were used on the library's stream must be released before the stream is
     # destroyed with the context (their allocator blocks record events on it when freed)
+    if world > 1:
+        lanes.clear()
     del d_sets, pinned, d_stage, d_part, d_all
     torch.cuda.synchronize()
     torch.cuda.empty_cache()
     bases.free()
-    if ctx2 is not None:
-        ctx2.close()
+    ctx2.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -80,6 +80,11 @@ int zk_msm_device(zk_ctx *ctx, const zk_bases *b, const void *d_scalars, size_t 
 int zk_msm_begin(zk_ctx *ctx, const zk_bases *b, const uint64_t *scalars, size_t n);
 int zk_msm_device_begin(zk_ctx *ctx, const zk_bases *b, const void *d_scalars, size_t n);
 int zk_msm_end(zk_ctx *ctx, uint8_t *out);
+/* multi-GPU form: the rank's partial (zk_partial_size bytes) lands in d_partial_out on zk_ctx_tail_stream(ctx); the caller enqueues
+ * its all-gather on that stream, then zk_points_fold_begin (fold + encode + download on the same stream); zk_msm_end collects. */
+void *zk_ctx_tail_stream(zk_ctx *ctx);
+int zk_msm_partial_device_begin(zk_ctx *ctx, const zk_bases *b, const void *d_scalars, size_t n, void *d_partial_out);
+int zk_points_fold_begin(zk_ctx *ctx, int group, const void *d_partials, size_t count);
 /* batch of `batch` independent scalar vectors (each n long, contiguous) against the same bases;
  * out: batch encodings.  Used by the batched prover. */
 int zk_msm_batch_device(zk_ctx *ctx, const zk_bases *b, const void *d_scalars, size_t n, size_t batch, uint8_t *out);

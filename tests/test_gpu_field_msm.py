@@ -255,3 +255,37 @@ def test_multiexp_future_matches_blocking_call():
         zk.multiexp_end(c2, b)                                      # nothing in flight
     assert zk.multiexp(b, sets[2]) == want[2]                       # the blocking call still works on the same context
     b.free(); c2.close(); c1.close()
+
+
+def test_partial_futures_fold_like_two_ranks():
+    """The multi-GPU form of the future on one device: two 'ranks' hold the two halves of the bases, each produces its partial
+    with zk_msm_partial_device_begin, the partials are laid side by side (what the all-gather does) and folded with
+    zk_points_fold_begin; the result must equal the single MSM over all bases and the oracle."""
+    import torch
+    c1, c2 = zk.Context(0), zk.Context(0)
+    n = 1 << 13
+    bases = zk.scalar_mul_many(c1, 1, zk.G1_GENERATOR, sy.random_fr_limbs(n, 51))
+    scal = sy.random_fr_limbs(n, 52)
+    full = zk.Bases(c1, 1, bases)
+    want = zk.multiexp(full, scal)
+    assert want == co.g1_encode(co.g1_msm(bases, scal), False)
+    h = n // 2
+    halves = [zk.Bases(c1, 1, bases[:h]), zk.Bases(c1, 1, bases[h:])]
+    d = torch.from_numpy(scal.view(np.int64)).cuda()
+    psz = zk.partial_size(1)
+    gathered = torch.zeros(2 * psz, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    for r, c in enumerate((c1, c2)):
+        zk.multiexp_partial_device_begin(c, halves[r], d.data_ptr() + r * h * 32, h, gathered.data_ptr() + r * psz)
+    # rank 1's partial was written by another context's tail stream: order it before the fold (NCCL does this in bench.py)
+    torch.cuda.synchronize()
+    with pytest.raises(zk.ZkError):
+        zk.multiexp_end(c1, full)                                   # only a partial is in flight: nothing to collect yet
+    zk.points_fold_begin(c1, 1, gathered.data_ptr(), 2)
+    assert zk.multiexp_end(c1, full) == want
+    zk.points_fold_begin(c2, 1, gathered.data_ptr(), 2)             # the other rank folds the same gathered buffer
+    assert zk.multiexp_end(c2, full) == want
+    assert zk.tail_stream(c1) != 0 and zk.tail_stream(c1) != c1.stream
+    for b in halves + [full]:
+        b.free()
+    c2.close(); c1.close()

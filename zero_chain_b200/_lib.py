@@ -30,6 +30,9 @@ SIGNATURES = {
     "zk_msm_begin": (i32, [vp, vp, vp, sz]),
     "zk_msm_device_begin": (i32, [vp, vp, vp, sz]),
     "zk_msm_end": (i32, [vp, vp]),
+    "zk_ctx_tail_stream": (vp, [vp]),
+    "zk_msm_partial_device_begin": (i32, [vp, vp, vp, sz, vp]),
+    "zk_points_fold_begin": (i32, [vp, i32, vp, sz]),
     "zk_msm_batch_device": (i32, [vp, vp, vp, sz, sz, vp]),
     "zk_partial_size": (sz, [i32]),
     "zk_msm_partial_device": (i32, [vp, vp, vp, sz, vp]),

@@ -180,31 +180,76 @@ extern "C" int zk_msm(zk_ctx *ctx, const zk_bases *b, const uint64_t *scalars, s
     ZK_CUDA(cudaMemcpyAsync(ctx->scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
     return zk_msm_device(ctx, b, ctx->scalars.p, n, out);
 }
+template <class F>
+__global__ void k_fold_serial(const XYZZ<F> *in, int n, XYZZ<F> *out) {
+    if (threadIdx.x | blockIdx.x) return;
+    XYZZ<F> r = in[0];
+    for (int i = 1; i < n; i++) r.add(in[i]);
+    out[0] = r;
+}
 // ---- asynchronous MSM: bellman's multiexp returns a future (multiexp.rs); begin / end is that future on CUDA streams ----
-static int msm_begin_common(zk_ctx *ctx, const zk_bases *b, const void *d_scalars, size_t n) {
-    if (!ctx->tail) {
-        int lo = 0, hi = 0;
-        ZK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        ZK_CUDA(cudaStreamCreateWithPriority(&ctx->tail, cudaStreamNonBlocking, hi));
-        ZK_CUDA(cudaEventCreateWithFlags(&ctx->ev_front, cudaEventDisableTiming));
-        ZK_CUDA(cudaEventCreateWithFlags(&ctx->ev_tail, cudaEventDisableTiming));
-    }
-    const size_t per = b->group == 1 ? 96 : 192;
+static const size_t PARTIAL_IN_FLIGHT = ~(size_t)0;      // pending_bytes sentinel: a partial MSM is in flight, no host result yet
+static int ensure_tail(zk_ctx *ctx) {
+    if (ctx->tail) return ZK_OK;
+    int lo = 0, hi = 0;
+    ZK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    ZK_CUDA(cudaStreamCreateWithPriority(&ctx->tail, cudaStreamNonBlocking, hi));
+    ZK_CUDA(cudaEventCreateWithFlags(&ctx->ev_front, cudaEventDisableTiming));
+    ZK_CUDA(cudaEventCreateWithFlags(&ctx->ev_tail, cudaEventDisableTiming));
+    return ZK_OK;
+}
+extern "C" void *zk_ctx_tail_stream(zk_ctx *ctx) {
+    if (!ctx || zk_use_device(ctx) != ZK_OK || ensure_tail(ctx) != ZK_OK) return nullptr;
+    return (void *)ctx->tail;
+}
+// affine conversion + wire format + D2H of ctx->result[0] on the tail stream; the context's stream is ordered after it
+static int finish_on_tail(zk_ctx *ctx, int group) {
+    const size_t per = group == 1 ? 96 : 192;
     ZK_TRY(ctx->out_bytes.reserve(per));
-    ctx->split_tail = true;
-    int r = zk_msm_run(ctx, b, d_scalars, n, 1);
-    ctx->split_tail = false;
-    if (r) return r;
     cudaStream_t saved = ctx->stream;
-    ctx->stream = ctx->tail;                    // affine conversion + wire format + D2H stay on the tail stream
-    r = b->group == 1 ? zk_encode_results_g1(ctx, 1, 0, ctx->out_bytes.as<uint8_t>()) : encode_results_t<Fq2>(ctx, 1, 0, ctx->out_bytes.as<uint8_t>());
+    ctx->stream = ctx->tail;
+    int r = group == 1 ? zk_encode_results_g1(ctx, 1, 0, ctx->out_bytes.as<uint8_t>()) : encode_results_t<Fq2>(ctx, 1, 0, ctx->out_bytes.as<uint8_t>());
     ctx->stream = saved;
     if (r) return r;
     ZK_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->out_bytes.p, per, cudaMemcpyDeviceToHost, ctx->tail));
     ZK_CUDA(cudaEventRecord(ctx->ev_tail, ctx->tail));
-    ZK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_tail, 0));       // later work on the context's stream stays ordered after this MSM
+    ZK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_tail, 0));
     ctx->pending_bytes = per;
     return ZK_OK;
+}
+static int msm_split(zk_ctx *ctx, const zk_bases *b, const void *d_scalars, size_t n) {
+    ZK_TRY(ensure_tail(ctx));
+    ctx->split_tail = true;
+    int r = zk_msm_run(ctx, b, d_scalars, n, 1);
+    ctx->split_tail = false;
+    return r;
+}
+static int msm_begin_common(zk_ctx *ctx, const zk_bases *b, const void *d_scalars, size_t n) {
+    ZK_TRY(msm_split(ctx, b, d_scalars, n));
+    return finish_on_tail(ctx, b->group);
+}
+// multi-GPU form of the future: the rank's partial sum (XYZZ, zk_partial_size bytes) is left in d_partial_out by the tail stream;
+// the caller enqueues its all-gather on zk_ctx_tail_stream and then zk_points_fold_begin; zk_msm_end collects the folded result
+extern "C" int zk_msm_partial_device_begin(zk_ctx *ctx, const zk_bases *b, const void *d_scalars, size_t n, void *d_partial_out) {
+    if (!ctx || !b || !d_scalars || !d_partial_out) { zk_set_error("zk_msm_partial_device_begin: NULL argument"); return ZK_ERR_INVALID; }
+    if (ctx->pending_bytes) { zk_set_error("zk_msm_partial_device_begin: an MSM is already in flight on this context"); return ZK_ERR_INVALID; }
+    ZK_TRY(zk_use_device(ctx));
+    ZK_TRY(msm_split(ctx, b, d_scalars, n));
+    ZK_CUDA(cudaMemcpyAsync(d_partial_out, ctx->result.p, zk_partial_size(b->group), cudaMemcpyDeviceToDevice, ctx->tail));
+    ctx->pending_bytes = PARTIAL_IN_FLIGHT;
+    return ZK_OK;
+}
+extern "C" int zk_points_fold_begin(zk_ctx *ctx, int group, const void *d_partials, size_t count) {
+    if (!ctx || !d_partials || count == 0 || (group != 1 && group != 2)) { zk_set_error("zk_points_fold_begin: bad argument"); return ZK_ERR_INVALID; }
+    if (ctx->pending_bytes && ctx->pending_bytes != PARTIAL_IN_FLIGHT) { zk_set_error("zk_points_fold_begin: a result is already pending on this context"); return ZK_ERR_INVALID; }
+    ZK_TRY(zk_use_device(ctx));
+    ZK_TRY(ensure_tail(ctx));
+    ZK_TRY(ctx->result.reserve(4 * sizeof(G2XYZZ)));
+    if (group == 1) k_fold_serial<Fq><<<1, 32, 0, ctx->tail>>>((const G1XYZZ *)d_partials, (int)count, ctx->result.as<G1XYZZ>());
+    else k_fold_serial<Fq2><<<1, 32, 0, ctx->tail>>>((const G2XYZZ *)d_partials, (int)count, ctx->result.as<G2XYZZ>());
+    ZK_CUDA(cudaGetLastError());
+    ctx->pending_bytes = 0;
+    return finish_on_tail(ctx, group);
 }
 extern "C" int zk_msm_device_begin(zk_ctx *ctx, const zk_bases *b, const void *d_scalars, size_t n) {
     if (!ctx || !b || !d_scalars) { zk_set_error("zk_msm_device_begin: NULL argument"); return ZK_ERR_INVALID; }
@@ -222,7 +267,7 @@ extern "C" int zk_msm_begin(zk_ctx *ctx, const zk_bases *b, const uint64_t *scal
 }
 extern "C" int zk_msm_end(zk_ctx *ctx, uint8_t *out) {
     if (!ctx || !out) { zk_set_error("zk_msm_end: NULL argument"); return ZK_ERR_INVALID; }
-    if (!ctx->pending_bytes) { zk_set_error("zk_msm_end: no MSM in flight"); return ZK_ERR_INVALID; }
+    if (!ctx->pending_bytes || ctx->pending_bytes == PARTIAL_IN_FLIGHT) { zk_set_error("zk_msm_end: no result in flight"); return ZK_ERR_INVALID; }
     ZK_TRY(zk_use_device(ctx));
     size_t per = ctx->pending_bytes;
     ctx->pending_bytes = 0;
@@ -237,13 +282,6 @@ extern "C" int zk_msm_partial_device(zk_ctx *ctx, const zk_bases *b, const void 
     ZK_TRY(zk_msm_run(ctx, b, d_scalars, n, 1));
     ZK_CUDA(cudaMemcpyAsync(d_partial_out, ctx->result.p, zk_partial_size(b->group), cudaMemcpyDeviceToDevice, ctx->stream));
     return zk_check_err_flag(ctx);
-}
-template <class F>
-__global__ void k_fold_serial(const XYZZ<F> *in, int n, XYZZ<F> *out) {
-    if (threadIdx.x | blockIdx.x) return;
-    XYZZ<F> r = in[0];
-    for (int i = 1; i < n; i++) r.add(in[i]);
-    out[0] = r;
 }
 extern "C" int zk_points_fold(zk_ctx *ctx, int group, const void *d_partials, size_t count, uint8_t *out) {
     if (!ctx || !d_partials || !out || count == 0) { zk_set_error("zk_points_fold: bad argument"); return ZK_ERR_INVALID; }

@@ -133,6 +133,19 @@ def multiexp_device_begin(ctx: Context, bases: Bases, d_scalars_ptr: int, n: int
     _ck(_lib.lib().zk_msm_device_begin(ctx._h, bases._h, C.c_void_p(d_scalars_ptr), n))
 
 
+def multiexp_partial_device_begin(ctx: Context, bases: Bases, d_scalars_ptr: int, n: int, d_out_ptr: int):
+    _ck(_lib.lib().zk_msm_partial_device_begin(ctx._h, bases._h, C.c_void_p(d_scalars_ptr), n, C.c_void_p(d_out_ptr)))
+
+
+def points_fold_begin(ctx: Context, group: int, d_partials_ptr: int, count: int):
+    _ck(_lib.lib().zk_points_fold_begin(ctx._h, group, C.c_void_p(d_partials_ptr), count))
+
+
+def tail_stream(ctx: Context) -> int:
+    """CUDA stream (high priority) on which a context finishes its futures; enqueue the all-gather of partials here."""
+    return int(_lib.lib().zk_ctx_tail_stream(ctx._h))
+
+
 def multiexp_end(ctx: Context, bases: Bases) -> bytes:
     out = np.zeros(96 if bases.group == 1 else 192, np.uint8)
     _ck(_lib.lib().zk_msm_end(ctx._h, _p(out)))
