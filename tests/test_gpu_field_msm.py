@@ -254,6 +254,13 @@ def test_multiexp_future_matches_blocking_call():
     with pytest.raises(zk.ZkError):
         zk.multiexp_end(c2, b)                                      # nothing in flight
     assert zk.multiexp(b, sets[2]) == want[2]                       # the blocking call still works on the same context
+    # a scalar >= r surfaces when the future is collected, as it does from the blocking call
+    bad = sets[3].copy(); bad[7] = co.ints_to_limbs([pr.R], 4)[0]
+    zk.multiexp_begin(c1, b, bad)
+    with pytest.raises(zk.SynthesisError) as e:
+        zk.multiexp_end(c1, b)
+    assert e.value.code == -8
+    assert zk.multiexp(b, sets[3]) == want[3]                       # and the context is usable afterwards
     b.free(); c2.close(); c1.close()
 
 
