@@ -15,6 +15,7 @@
 // which equals bellman's  delta*rs + alpha*s + beta*r + A*s + B1*r + H + L.  A whole batch of proofs
 // shares every launch: NTTs are batched (grid.y) and each MSM uses one window set per proof.
 #define ZK_SEMI_HOT 1   // Fq product inlined into the (noinline) point operations: shorter dependent chains in k_scale_points / k_finish_proofs
+#include <stdlib.h>
 #include "internal.h"
 #include "codec.cuh"
 
@@ -95,7 +96,9 @@ extern "C" int zk_params_load(zk_ctx *ctx, const uint8_t *buf, size_t len, int c
     p->device = ctx->device;
     p->n_ic = vcnt[0]; p->n_h = vcnt[1]; p->n_l = vcnt[2]; p->n_a = vcnt[3]; p->n_b1 = vcnt[4]; p->n_b2 = vcnt[5];
     // window tables (built once; the CRS is fixed)
-    if ((r = zk_bases_from_device(ctx, 1, dh, n_h, 0, 1, &p->h)) || (r = zk_bases_from_device(ctx, 1, dl, n_l, 0, 1, &p->l)) ||
+    int wb_h = 0;
+    if (const char *e = getenv("ZK_WB_H")) wb_h = atoi(e);          // experiment knob: window bits of the H-query tables (0 = automatic)
+    if ((r = zk_bases_from_device(ctx, 1, dh, n_h, wb_h, 1, &p->h)) || (r = zk_bases_from_device(ctx, 1, dl, n_l, 0, 1, &p->l)) ||
         (r = zk_bases_from_device(ctx, 1, da, n_a, 0, 1, &p->a)) || (r = zk_bases_from_device(ctx, 1, db1, n_b1, 0, 1, &p->b1)) ||
         (r = zk_bases_from_device(ctx, 2, db2, n_b2, 0, 1, &p->b2))) {
         zk_params_free(p);
