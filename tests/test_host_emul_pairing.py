@@ -125,7 +125,7 @@ def test_compressed_decode(emu):
     """decode_compressed (codec.cuh): square roots, sign selection, flag / range / subgroup rejections, against pyref."""
     rng = pr.SplitMix64(5)
     o1, o2 = np.zeros(24, np.uint32), np.zeros(48, np.uint32)
-    for _ in range(4):
+    for _ in range(12):             # enough points to hit both branches of the Fq2 square root (d square / non-square)
         k = rng.below(pr.R, 4) or 1
         for neg in (False, True):
             p = pr.ec_mul(pr.FQ, pr.G1_GEN, k)

@@ -143,9 +143,11 @@ static ZK_PTFN bool fq_sqrt(Fq &out, const Fq &a) {
     return s.sqr() == a;
 }
 ZK_DEV bool field_sqrt(Fq &out, const Fq &a) { return fq_sqrt(out, a); }
-// Fq2 root through the norm: for a = a0 + a1 u with a1 != 0, n = sqrt(a0^2 + a1^2), x^2 = (a0 +- n)/2, y = a1 / (2x).
-// (The reference uses Algorithm 9 of eprint 2012/685, fq2.rs:160-214; any root serves because the caller fixes the sign
-// from the encoding's flag.)
+// Fq2 root through the norm, two Fq exponentiations and no inversion: for a = a0 + a1 u with a1 != 0 let n = sqrt(a0^2 + a1^2),
+// d = (a0 + n)/2 and t = d^((q-3)/4), x = t d.  If d is a square, t^2 d = 1, so x^2 = d and 1/x = t: the root is (x, a1 t / 2).
+// Otherwise t^2 d = -1, the other candidate d' = d - n = -(a1/2)^2 / d is a square with root a1 t / 2, and a1 / (2 * that) = 1/t = -x:
+// the root is (a1 t / 2, -x).  (The reference uses Algorithm 9 of eprint 2012/685, fq2.rs:160-214; any root serves because the caller
+// fixes the sign from the encoding's flag.)
 static ZK_PTFN bool field_sqrt(Fq2 &out, const Fq2 &a) {
     Fq2 r = Fq2::zero();
     bool ok = false;
@@ -156,14 +158,21 @@ static ZK_PTFN bool field_sqrt(Fq2 &out, const Fq2 &a) {
     } else {
         Fq n;
         if (fq_sqrt(n, a.c0.sqr() + a.c1.sqr())) {
-            Fq two = Fq::one().dbl(), half = two.inverse();
-            Fq d = (a.c0 + n) * half, x;
-            bool got = fq_sqrt(x, d);
-            if (!got) { d = d - n; got = fq_sqrt(x, d); }
-            if (got && !x.is_zero()) {
-                r.c0 = x; r.c1 = a.c1 * x.dbl().inverse();
-                ok = r.sqr() == a;
-            }
+            uint32_t e[12];
+            Fq half;                                       // (q + 1) / 2 as a field element = 1/2
+            for (int i = 0; i < 12; i++) e[i] = FqParams::mod(i);
+            e[0] += 1;
+            for (int i = 0; i < 11; i++) half.l[i] = (e[i] >> 1) | (e[i + 1] << 31);
+            half.l[11] = e[11] >> 1;
+            half = Fq::from_canonical(half);
+            e[0] -= 4;                                     // q - 3
+            for (int i = 0; i < 11; i++) e[i] = (e[i] >> 2) | (e[i + 1] << 30);
+            e[11] >>= 2;
+            Fq d = (a.c0 + n) * half;
+            Fq t = d.pow(e, 12), x = t * d, w = a.c1 * t * half;
+            if (x.sqr() == d) { r.c0 = x; r.c1 = w; }
+            else { r.c0 = w; r.c1 = x.neg(); }
+            ok = r.sqr() == a;
         }
     }
     out = r;
