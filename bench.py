@@ -298,6 +298,9 @@ def run_ours(args):
         "avg_launch_ms": acc_avg_s * 1e3, "launches": acc_launches, "share_of_step": acc_ms / ms_dev,
         # the convention above counts 11 products x 16 windows per term; the kernel actually executes 10 products (XYZZ mixed
         # addition) x W windows per term, so with W = 13 (20-bit windows) `frac` can exceed 1 — `executed_frac` is the pipe efficiency
+        "note": "frac uses SURVEY 8(d)'s fixed algorithmic count (176 products per term = 11 x 16 windows); the kernel executes "
+                "10 x %d per term (XYZZ mixed addition, %d-bit windows from precomputed tables), so frac can exceed 1 — executed_frac is "
+                "the pipe efficiency of the kernel as run" % (255 // bases.window_bits + 1, bases.window_bits),
         "executed_modmul_per_launch": 10 * n * (255 // bases.window_bits + 1),
         "executed_frac": 10 * n * (255 // bases.window_bits + 1) / acc_avg_s / modmul_peak,
         "whole_msm_frac": ALGO_MODMUL_PER_TERM * total_terms * args.steps / (ms_dev * 1e-3) / (modmul_peak * world),
