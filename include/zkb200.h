@@ -19,8 +19,10 @@
  *   - every function returns ZK_OK (0) or a negative error; zk_last_error() gives the text.
  *     Error codes mirror bellman's SynthesisError / io::Error as seen at the call sites
  *     (zface/src/error.rs:17,45-48).
- *   - thread safety: a zk_ctx is single-threaded (one CUDA stream); zk_params / zk_bases are
- *     read-only after creation and may be shared by several contexts on the same device.
+ *   - thread safety: a zk_ctx is single-threaded (one CUDA stream + its own workspace, NTT tables and lanes); zk_params /
+ *     zk_bases / zk_pvk / zk_r1cs are read-only after creation and may be shared by several contexts on the same device.
+ *     Concurrent proving on one zk_params (what bellman's Arc<Vec<..>> parameters allow) = one zk_ctx per
+ *     host thread, all passing the same zk_params (bench.py's two_batches_in_flight does exactly that).
  *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
  *     ZK_ERR_CUDA.
  */
@@ -116,6 +118,21 @@ int zk_params_load(zk_ctx *ctx, const uint8_t *pk_bytes, size_t len, int checked
 void zk_params_free(zk_params *p);
 /* counts[6] = { ic, h, l, a, b_g1, b_g2 } */
 int zk_params_counts(const zk_params *p, uint64_t counts[6]);
+/* Parameters::write (bellman groth16; reference call core/proofs/src/confidential.rs:73-93 `self.proving_key.write(..)`): the
+ * resident CRS re-encoded as the exact byte stream Parameters::read consumes — zk_params_size bytes; loading a file and writing
+ * it back reproduces the file byte for byte.  zk_params_write_vk emits only the VerifyingKey head (VerifyingKey::write: alpha_g1 |
+ * beta_g1 | beta_g2 | gamma_g2 | delta_g1 | delta_g2 | u32 n | ic; zk_params_vk_size bytes) — what `params.vk`
+ * (core/proofs/src/setup.rs:31, prepare_verifying_key(&params.vk)) needs on the host side. */
+size_t zk_params_size(const zk_params *p);
+size_t zk_params_vk_size(const zk_params *p);
+int zk_params_write(zk_ctx *ctx, const zk_params *p, uint8_t *out);
+int zk_params_write_vk(zk_ctx *ctx, const zk_params *p, uint8_t *out);
+/* Parameters::read(buf, checked = true) with a decoded-CRS cache on disk (the "FIX: too heavy" read at
+ * core/proofs/src/crypto_components.rs:320-328).  If `cache_path` holds the decoded Montgomery points of exactly these bytes
+ * (SHA-256 of the whole stream, length and vector counts are compared), they are uploaded as they are — no decoding, no on-curve
+ * or subgroup tests (*cache_hit = 1).  Otherwise the stream goes through the full CHECKED load and the cache file is (re)written
+ * atomically (*cache_hit = 0); a cache that cannot be written is not an error.  cache_hit may be NULL. */
+int zk_params_load_cached(zk_ctx *ctx, const uint8_t *pk_bytes, size_t len, const char *cache_path, int *cache_hit, zk_params **out);
 
 /* create_proof for ONE already-synthesised witness (the Rust shim runs ProvingAssignment::synthesize
  * and the `input_i * 0 = 0` rows, then calls this).

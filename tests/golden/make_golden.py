@@ -94,6 +94,10 @@ def main():
         n_ic = int.from_bytes(pkb[864:868], "big")
         open(os.path.join(here, "%s_vk_head.bin" % name), "wb").write(pkb[:868 + 96 * n_ic])
         open(os.path.join(here, "%s_pvk.dat" % name), "wb").write(open(os.path.join(REF, "zface/params/%s_vk.dat" % name), "rb").read())
+    # the shipped confidential-transfer CRS itself (10 133 592 B, 93 124 points): the GPU box has no /root/reference, and
+    # Parameters::read(&pk_buf[..], true) on exactly these bytes (core/proofs/src/confidential.rs:95-103) is what the
+    # device loader replaces — tests/test_gpu_real_crs.py loads it, proves on it and round-trips it through zk_params_write
+    open(os.path.join(here, "conf_pk.dat"), "wb").write(open(os.path.join(REF, "zface/params/conf_pk.dat"), "rb").read())
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "kats.json")
     json.dump(res, open(out, "w"), indent=1)
     print("wrote", out, {k: len(v["groups"]) for k, v in res["tests"].items()})

@@ -194,11 +194,11 @@ def test_verify_full_batch_round_trip(ctx):
         inputs[i][i % 3] = (inputs[i][i % 3] + 1) % pr.R
     want = [0 if i in flip else 1 for i in range(n)]
     assert zk.verify_proofs(pvk, proofs, inputs) == want
-    os.environ["ZK_VERIFY_CHUNK"] = "100"            # the slicing path of very large batches (default slice: 2^18 proofs)
-    try:
-        assert zk.verify_proofs(pvk, proofs, inputs) == want
-    finally:
-        del os.environ["ZK_VERIFY_CHUNK"]
+    # the slicing path of very large batches (slice: 2^18 proofs): 2^18 + 333 proofs, the tampered pattern continued
+    big = (1 << 18) + 333
+    reps = (big + n - 1) // n
+    got = zk.verify_proofs(pvk, (proofs * reps)[:192 * big], (inputs * reps)[:big])
+    assert got == (want * reps)[:big]
     pvk.free(); params.free()
 
 

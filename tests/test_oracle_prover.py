@@ -160,13 +160,14 @@ def test_params_read_errors():
 
 
 def test_shipped_crs_parses():
-    """Parameters grammar vs the reference's shipped CRS (only where /root/reference exists — this
-    container; the GPU box never sees it).  SURVEY.md §3.3: the grammar must consume all bytes."""
+    """Parameters grammar vs the reference's shipped CRS (tests/golden/conf_pk.dat, copied from zface/params/conf_pk.dat by
+    tests/golden/make_golden.py, so the GPU box sees the same bytes).  SURVEY.md §3.3: the grammar must consume all bytes."""
     import hashlib, json, os
-    path = "/root/reference/zface/params/conf_pk.dat"
-    if not os.path.exists(path):
-        pytest.skip("reference tree not present")
+    path = os.path.join(os.path.dirname(__file__), "golden", "conf_pk.dat")
     buf = open(path, "rb").read()
+    ref = "/root/reference/zface/params/conf_pk.dat"
+    if os.path.exists(ref):
+        assert open(ref, "rb").read() == buf
     K = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kats.json")))
     assert hashlib.sha256(buf).hexdigest() == K["files"]["zface/params/conf_pk.dat"]["sha256"]
     lay = pr.params_layout(buf)

@@ -42,6 +42,11 @@ SIGNATURES = {
     "zk_params_load": (i32, [vp, vp, sz, i32, PP]),
     "zk_params_free": (None, [vp]),
     "zk_params_counts": (i32, [vp, vp]),
+    "zk_params_size": (sz, [vp]),
+    "zk_params_vk_size": (sz, [vp]),
+    "zk_params_write": (i32, [vp, vp, vp]),
+    "zk_params_write_vk": (i32, [vp, vp, vp]),
+    "zk_params_load_cached": (i32, [vp, vp, sz, C.c_char_p, C.POINTER(i32), PP]),
     "zk_groth16_prove": (i32, [vp, vp, vp, vp, vp, sz, vp, sz, vp, sz, vp, vp, vp, vp, vp, vp]),
     "zk_groth16_prove_batch": (i32, [vp, vp, sz, vp, vp, vp, sz, vp, sz, vp, sz, vp, vp, vp, vp, vp, vp]),
     "zk_r1cs_load": (i32, [vp, sz, sz, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp, PP]),

@@ -123,6 +123,10 @@ ZK_DEV int decode_uncompressed(Affine<F> &p, const uint8_t *in, bool checked) {
     }
     if (b0 & 0x20) return DEC_UNEXPECTED_INFO;
     if (!load_coord(p.x, in, 0x1f) || !load_coord(p.y, in + CB, 0xff)) return DEC_COORD;
+    // (0, 0) without the infinity flag: the reference's into_affine answers NotOnCurve (0 != 4, ec.rs:675-685).  Internally the
+    // all-zero pattern MEANS infinity, so it must never be produced by this branch — rejected in unchecked mode as well
+    // (into_affine_unchecked would hand the garbage point on; DESIGN.md §1, deviations).
+    if (p.is_inf()) return DEC_NOT_ON_CURVE;
     if (checked) {
         if (!on_curve(p)) return DEC_NOT_ON_CURVE;
         if (!in_subgroup(p)) return DEC_NOT_IN_SUBGROUP;
@@ -208,6 +212,13 @@ __global__ void k_encode_xyzz(const XYZZ<F> *__restrict__ in, int n, int compres
     constexpr int CB = CoordBytes<F>::N;
     Affine<F> a = in[i].to_affine();
     encode_point(out + (size_t)i * (compressed ? CB : 2 * CB), a, compressed != 0);
+}
+// n affine points (limb form) -> Uncompressed encodings (Parameters::write, bellman groth16/mod.rs; G1Uncompressed::from_affine ec.rs:686-700)
+template <class F>
+__global__ void __launch_bounds__(128) k_encode_affine(const Affine<F> *__restrict__ in, size_t n, uint8_t *__restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    encode_point(out + i * 2 * CoordBytes<F>::N, in[i], false);
 }
 // decode n uncompressed points; err receives the first non-zero code seen (atomicCAS); reject_inf for query vectors
 template <class F>

@@ -23,6 +23,10 @@ struct zk_params {
     int device = 0;
     uint64_t n_ic = 0, n_h = 0, n_l = 0, n_a = 0, n_b1 = 0, n_b2 = 0;
     zk_bases *h = nullptr, *l = nullptr, *a = nullptr, *b1 = nullptr, *b2 = nullptr;   // extended vectors (see above)
+    // the VerifyingKey part, kept so that Parameters::write and `params.vk` (core/proofs/src/setup.rs:31) can be served from the
+    // resident CRS: G1 = alpha_g1, beta_g1, delta_g1, ic[n_ic]; G2 = beta_g2, gamma_g2, delta_g2 (affine, Montgomery)
+    G1Affine *d_vk1 = nullptr;
+    G2Affine *d_vk2 = nullptr;
 };
 
 // The fixed constraint system of one circuit, resident on the device in CSR form.
@@ -35,10 +39,14 @@ struct zk_r1cs {
 };
 
 static uint32_t rd_u32be(const uint8_t *p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+static void wr_u32be(uint8_t *p, uint32_t v) { p[0] = (uint8_t)(v >> 24); p[1] = (uint8_t)(v >> 16); p[2] = (uint8_t)(v >> 8); p[3] = (uint8_t)v; }
 
 extern "C" void zk_params_free(zk_params *p) {
     if (!p) return;
     zk_bases_free(p->h); zk_bases_free(p->l); zk_bases_free(p->a); zk_bases_free(p->b1); zk_bases_free(p->b2);
+    cudaSetDevice(p->device);
+    if (p->d_vk1) cudaFree(p->d_vk1);
+    if (p->d_vk2) cudaFree(p->d_vk2);
     delete p;
 }
 extern "C" int zk_params_counts(const zk_params *p, uint64_t c[6]) {
@@ -47,13 +55,51 @@ extern "C" int zk_params_counts(const zk_params *p, uint64_t c[6]) {
     return ZK_OK;
 }
 
-extern "C" int zk_params_load(zk_ctx *ctx, const uint8_t *buf, size_t len, int checked, zk_params **out) {
-    if (!ctx || !buf || !out) { zk_set_error("zk_params_load: NULL argument"); return ZK_ERR_INVALID; }
-    ZK_TRY(zk_use_device(ctx));
-    // ---- host: walk the grammar to find the vectors; no arithmetic here ----
-    const size_t VK_FIXED = 96 + 96 + 192 + 192 + 96 + 192;
+static const size_t VK_FIXED = 96 + 96 + 192 + 192 + 96 + 192;   // alpha_g1 | beta_g1 | beta_g2 | gamma_g2 | delta_g1 | delta_g2
+static const uint32_t CRS_POINT_LIMIT = 1u << 26;                // zk_bases_from_device accepts < 2^27 bases
+
+// Device-side layout of a decoded CRS before the tables are built: the five EXTENDED query vectors and the vk points.
+// g1 = h' | l | a' | b_g1' | vk1 (alpha, beta_g1, delta, ic...),  g2 = b_g2' | vk2 (beta_g2, gamma_g2, delta_g2)
+struct CrsLayout {
+    size_t cnt[6];                               // ic, h, l, a, b_g1, b_g2 as stored in the stream
+    size_t n_h, n_l, n_a, n_b1, n_b2, n_vk1;     // extended lengths
+    size_t o_h, o_l, o_a, o_b1, o_vk1;           // offsets (points) inside g1
+    size_t g1_total, g2_total;
+    explicit CrsLayout(const size_t c[6]) {
+        for (int k = 0; k < 6; k++) cnt[k] = c[k];
+        n_h = c[1] + 1; n_l = c[2]; n_a = c[3] + 2; n_b1 = c[4] + 2; n_b2 = c[5] + 2; n_vk1 = 3 + c[0];
+        o_h = 0; o_l = o_h + n_h; o_a = o_l + n_l; o_b1 = o_a + n_a; o_vk1 = o_b1 + n_b1;
+        g1_total = o_vk1 + n_vk1; g2_total = n_b2 + 3;
+    }
+};
+// tables + handle from decoded device arrays (shared by the byte-stream loader and the decoded-CRS cache)
+static int params_from_device(zk_ctx *ctx, const CrsLayout &L, const G1Affine *g1, const G2Affine *g2, zk_params **out) {
+    zk_params *p = new zk_params();
+    p->device = ctx->device;
+    p->n_ic = L.cnt[0]; p->n_h = L.cnt[1]; p->n_l = L.cnt[2]; p->n_a = L.cnt[3]; p->n_b1 = L.cnt[4]; p->n_b2 = L.cnt[5];
+    int r = ZK_OK;
+    if (cudaMalloc(&p->d_vk1, L.n_vk1 * sizeof(G1Affine)) != cudaSuccess || cudaMalloc(&p->d_vk2, 3 * sizeof(G2Affine)) != cudaSuccess) {
+        zk_set_error("cudaMalloc (verifying key) failed"); zk_params_free(p); return ZK_ERR_CUDA;
+    }
+    cudaMemcpyAsync(p->d_vk1, g1 + L.o_vk1, L.n_vk1 * sizeof(G1Affine), cudaMemcpyDeviceToDevice, ctx->stream);
+    cudaMemcpyAsync(p->d_vk2, g2 + L.n_b2, 3 * sizeof(G2Affine), cudaMemcpyDeviceToDevice, ctx->stream);
+    // window tables (built once; the CRS is fixed)
+    int wb_h = 0;
+#ifdef ZK_EXPERIMENTS
+    if (const char *e = getenv("ZK_WB_H")) wb_h = atoi(e);          // experiment knob: window bits of the H-query tables (0 = automatic)
+#endif
+    if ((r = zk_bases_from_device(ctx, 1, g1 + L.o_h, L.n_h, wb_h, 1, &p->h)) || (r = zk_bases_from_device(ctx, 1, g1 + L.o_l, L.n_l, 0, 1, &p->l)) ||
+        (r = zk_bases_from_device(ctx, 1, g1 + L.o_a, L.n_a, 0, 1, &p->a)) || (r = zk_bases_from_device(ctx, 1, g1 + L.o_b1, L.n_b1, 0, 1, &p->b1)) ||
+        (r = zk_bases_from_device(ctx, 2, g2, L.n_b2, 0, 1, &p->b2))) {
+        zk_params_free(p);
+        return r;
+    }
+    *out = p;
+    return ZK_OK;
+}
+// host: walk the grammar to find the vectors; no arithmetic here
+static int params_walk(const uint8_t *buf, size_t len, size_t voff[6], size_t vcnt[6]) {
     size_t off = VK_FIXED;
-    size_t voff[6], vcnt[6];
     const size_t vsz[6] = {96, 96, 96, 96, 96, 192};
     for (int k = 0; k < 6; k++) {
         if (off + 4 > len) { zk_set_error("Parameters stream truncated (length prefix %d)", k); return ZK_ERR_IO; }
@@ -63,17 +109,19 @@ extern "C" int zk_params_load(zk_ctx *ctx, const uint8_t *buf, size_t len, int c
         off += vcnt[k] * vsz[k];
     }
     if (vcnt[1] == 0 || vcnt[2] == 0 || vcnt[3] == 0 || vcnt[4] == 0 || vcnt[5] == 0) { zk_set_error("empty query vector in Parameters"); return ZK_ERR_IO; }
-    // ---- device: decode ----
+    for (int k = 0; k < 6; k++) if (vcnt[k] >= CRS_POINT_LIMIT) { zk_set_error("Parameters vector %d too long (%zu points)", k, vcnt[k]); return ZK_ERR_IO; }
+    return ZK_OK;
+}
+// decode the stream into stage_b (G1) / stage_c (G2) in the CrsLayout order
+static int params_decode(zk_ctx *ctx, const uint8_t *buf, size_t len, int checked, const size_t voff[6], const CrsLayout &L) {
     ZK_TRY(ctx->stage_a.reserve(len));
     ZK_CUDA(cudaMemcpyAsync(ctx->stage_a.p, buf, len, cudaMemcpyHostToDevice, ctx->stream));
     const uint8_t *d = ctx->stage_a.as<uint8_t>();
-    // extended vectors laid out in stage_b (G1) / stage_c (G2)
-    const size_t n_h = vcnt[1] + 1, n_l = vcnt[2], n_a = vcnt[3] + 2, n_b1 = vcnt[4] + 2, n_b2 = vcnt[5] + 2;
-    ZK_TRY(ctx->stage_b.reserve((n_h + n_l + n_a + n_b1 + vcnt[0] + 8) * sizeof(G1Affine)));
-    ZK_TRY(ctx->stage_c.reserve((n_b2 + 8) * sizeof(G2Affine)));
+    ZK_TRY(ctx->stage_b.reserve((L.g1_total + 8) * sizeof(G1Affine)));
+    ZK_TRY(ctx->stage_c.reserve((L.g2_total + 8) * sizeof(G2Affine)));
     G1Affine *g1 = ctx->stage_b.as<G1Affine>();
-    G1Affine *dh = g1, *dl = dh + n_h, *da = dl + n_l, *db1 = da + n_a, *dic = db1 + n_b1;
-    G2Affine *db2 = ctx->stage_c.as<G2Affine>();
+    G1Affine *dh = g1 + L.o_h, *dl = g1 + L.o_l, *da = g1 + L.o_a, *db1 = g1 + L.o_b1, *dvk = g1 + L.o_vk1;
+    G2Affine *db2 = ctx->stage_c.as<G2Affine>(), *dvk2 = db2 + L.n_b2;
     int *err = ctx->d_err + 1;
     auto dec1 = [&](size_t boff, size_t n, G1Affine *dst, int reject_inf) {
         if (n) zkcodec::k_decode_uncompressed<Fq><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(d + boff, n, checked, reject_inf, dst, err);
@@ -81,30 +129,173 @@ extern "C" int zk_params_load(zk_ctx *ctx, const uint8_t *buf, size_t len, int c
     auto dec2 = [&](size_t boff, size_t n, G2Affine *dst, int reject_inf) {
         if (n) zkcodec::k_decode_uncompressed<Fq2><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(d + boff, n, checked, reject_inf, dst, err);
     };
+    const size_t *vcnt = L.cnt;
     // vk: alpha_g1 @0, beta_g1 @96, beta_g2 @192, gamma_g2 @384, delta_g1 @576, delta_g2 @672
     dec1(voff[1], vcnt[1], dh, 1);          dec1(576, 1, dh + vcnt[1], 1);                                  // h ++ [delta_g1]
     dec1(voff[2], vcnt[2], dl, 1);
     dec1(voff[3], vcnt[3], da, 1);          dec1(0, 1, da + vcnt[3], 1);    dec1(576, 1, da + vcnt[3] + 1, 1);   // a ++ [alpha, delta]
     dec1(voff[4], vcnt[4], db1, 1);         dec1(96, 1, db1 + vcnt[4], 1);  dec1(576, 1, db1 + vcnt[4] + 1, 1);  // b_g1 ++ [beta_g1, delta]
     dec2(voff[5], vcnt[5], db2, 1);         dec2(192, 1, db2 + vcnt[5], 1); dec2(672, 1, db2 + vcnt[5] + 1, 1);  // b_g2 ++ [beta_g2, delta_g2]
-    dec1(voff[0], vcnt[0], dic, 0);                                                                       // ic: decoded (validated) only
-    dec2(384, 1, db2 + n_b2, 0);                                                                          // gamma_g2: validated only
+    // verifying key as it stands in the stream (already validated above where it overlaps): alpha, beta_g1, delta, ic | beta_g2, gamma_g2, delta_g2
+    dec1(0, 1, dvk, 1); dec1(96, 1, dvk + 1, 1); dec1(576, 1, dvk + 2, 1);
+    dec1(voff[0], vcnt[0], dvk + 3, 0);                                                                   // ic: infinity allowed (bellman reads it as is)
+    dec2(192, 1, dvk2, 1); dec2(384, 1, dvk2 + 1, 0); dec2(672, 1, dvk2 + 2, 1);                           // gamma_g2: not used by the prover
     ZK_CUDA(cudaGetLastError());
-    int r = zk_check_err_flag(ctx);
-    if (r) return r == ZK_ERR_DECODE ? ZK_ERR_DECODE : r;
-    zk_params *p = new zk_params();
-    p->device = ctx->device;
-    p->n_ic = vcnt[0]; p->n_h = vcnt[1]; p->n_l = vcnt[2]; p->n_a = vcnt[3]; p->n_b1 = vcnt[4]; p->n_b2 = vcnt[5];
-    // window tables (built once; the CRS is fixed)
-    int wb_h = 0;
-    if (const char *e = getenv("ZK_WB_H")) wb_h = atoi(e);          // experiment knob: window bits of the H-query tables (0 = automatic)
-    if ((r = zk_bases_from_device(ctx, 1, dh, n_h, wb_h, 1, &p->h)) || (r = zk_bases_from_device(ctx, 1, dl, n_l, 0, 1, &p->l)) ||
-        (r = zk_bases_from_device(ctx, 1, da, n_a, 0, 1, &p->a)) || (r = zk_bases_from_device(ctx, 1, db1, n_b1, 0, 1, &p->b1)) ||
-        (r = zk_bases_from_device(ctx, 2, db2, n_b2, 0, 1, &p->b2))) {
-        zk_params_free(p);
-        return r;
+    return zk_check_err_flag(ctx);
+}
+
+extern "C" int zk_params_load(zk_ctx *ctx, const uint8_t *buf, size_t len, int checked, zk_params **out) {
+    if (!ctx || !buf || !out) { zk_set_error("zk_params_load: NULL argument"); return ZK_ERR_INVALID; }
+    ZK_TRY(zk_use_device(ctx));
+    size_t voff[6], vcnt[6];
+    ZK_TRY(params_walk(buf, len, voff, vcnt));
+    CrsLayout L(vcnt);
+    ZK_TRY(params_decode(ctx, buf, len, checked, voff, L));
+    return params_from_device(ctx, L, ctx->stage_b.as<G1Affine>(), ctx->stage_c.as<G2Affine>(), out);
+}
+
+// ---- Parameters::write from the resident CRS --------------------------------------------------------------------------
+// (bellman groth16 Parameters::write: vk.write, then h, l, a, b_g1, b_g2 each as u32 BE length + uncompressed points; reference call
+// core/proofs/src/confidential.rs:83 `self.proving_key.write(&mut &mut v_pk)`.)  The device holds canonical affine points in
+// Montgomery form, and the Uncompressed encoding of a point is unique, so decode -> encode reproduces the input stream byte for byte.
+extern "C" size_t zk_params_size(const zk_params *p) {
+    if (!p) return 0;
+    return VK_FIXED + 4 + 96 * p->n_ic + 4 + 96 * p->n_h + 4 + 96 * p->n_l + 4 + 96 * p->n_a + 4 + 96 * p->n_b1 + 4 + 192 * p->n_b2;
+}
+extern "C" size_t zk_params_vk_size(const zk_params *p) { return p ? VK_FIXED + 4 + 96 * p->n_ic : 0; }
+static int params_write_impl(zk_ctx *ctx, const zk_params *p, uint8_t *out, bool vk_only) {
+    if (!ctx || !p || !out) { zk_set_error("zk_params_write: NULL argument"); return ZK_ERR_INVALID; }
+    if (p->device != ctx->device) { zk_set_error("params live on device %d, context on %d", p->device, ctx->device); return ZK_ERR_INVALID; }
+    ZK_TRY(zk_use_device(ctx));
+    const size_t total = vk_only ? zk_params_vk_size(p) : zk_params_size(p);
+    ZK_TRY(ctx->stage_a.reserve(total));
+    uint8_t *d = ctx->stage_a.as<uint8_t>();
+    cudaStream_t st = ctx->stream;
+    auto enc1 = [&](const G1Affine *src, size_t n, size_t boff) {
+        if (n) zkcodec::k_encode_affine<Fq><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(src, n, d + boff);
+    };
+    auto enc2 = [&](const G2Affine *src, size_t n, size_t boff) {
+        if (n) zkcodec::k_encode_affine<Fq2><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(src, n, d + boff);
+    };
+    enc1(p->d_vk1, 1, 0); enc1(p->d_vk1 + 1, 1, 96); enc2(p->d_vk2, 1, 192); enc2(p->d_vk2 + 1, 1, 384); enc1(p->d_vk1 + 2, 1, 576); enc2(p->d_vk2 + 2, 1, 672);
+    size_t off = VK_FIXED, pre[6];
+    pre[0] = off; off += 4; enc1(p->d_vk1 + 3, p->n_ic, off); off += 96 * p->n_ic;
+    if (!vk_only) {
+        pre[1] = off; off += 4; enc1((const G1Affine *)p->h->d_tbl, p->n_h, off); off += 96 * p->n_h;
+        pre[2] = off; off += 4; enc1((const G1Affine *)p->l->d_tbl, p->n_l, off); off += 96 * p->n_l;
+        pre[3] = off; off += 4; enc1((const G1Affine *)p->a->d_tbl, p->n_a, off); off += 96 * p->n_a;
+        pre[4] = off; off += 4; enc1((const G1Affine *)p->b1->d_tbl, p->n_b1, off); off += 96 * p->n_b1;
+        pre[5] = off; off += 4; enc2((const G2Affine *)p->b2->d_tbl, p->n_b2, off); off += 192 * p->n_b2;
     }
-    *out = p;
+    ZK_CUDA(cudaGetLastError());
+    ZK_CUDA(cudaMemcpyAsync(out, d, total, cudaMemcpyDeviceToHost, st));
+    ZK_CUDA(cudaStreamSynchronize(st));
+    const uint64_t cnt[6] = {p->n_ic, p->n_h, p->n_l, p->n_a, p->n_b1, p->n_b2};
+    for (int k = 0; k < (vk_only ? 1 : 6); k++) wr_u32be(out + pre[k], (uint32_t)cnt[k]);
+    return ZK_OK;
+}
+extern "C" int zk_params_write(zk_ctx *ctx, const zk_params *p, uint8_t *out) { return params_write_impl(ctx, p, out, false); }
+extern "C" int zk_params_write_vk(zk_ctx *ctx, const zk_params *p, uint8_t *out) { return params_write_impl(ctx, p, out, true); }
+
+// ---- decoded-CRS cache on disk (the "FIX: too heavy" read at core/proofs/src/crypto_components.rs:320) --------------
+// First load of a proving key: zk_params_load(checked) + the decoded Montgomery points written to `cache_path`.  Later loads of the
+// SAME bytes (SHA-256 guard over the whole stream) upload the decoded points directly: no decoding, no on-curve / subgroup tests.
+namespace {
+struct Sha256 {
+    uint32_t h[8]; uint8_t blk[64]; size_t fill = 0; uint64_t total = 0;
+    Sha256() { static const uint32_t iv[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u}; memcpy(h, iv, 32); }
+    static uint32_t ror(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+    void block(const uint8_t *p) {
+        static const uint32_t K[64] = {
+            0x428a2f98u, 0x71374491u, 0xb5c0fbcfu, 0xe9b5dba5u, 0x3956c25bu, 0x59f111f1u, 0x923f82a4u, 0xab1c5ed5u, 0xd807aa98u, 0x12835b01u, 0x243185beu, 0x550c7dc3u,
+            0x72be5d74u, 0x80deb1feu, 0x9bdc06a7u, 0xc19bf174u, 0xe49b69c1u, 0xefbe4786u, 0x0fc19dc6u, 0x240ca1ccu, 0x2de92c6fu, 0x4a7484aau, 0x5cb0a9dcu, 0x76f988dau,
+            0x983e5152u, 0xa831c66du, 0xb00327c8u, 0xbf597fc7u, 0xc6e00bf3u, 0xd5a79147u, 0x06ca6351u, 0x14292967u, 0x27b70a85u, 0x2e1b2138u, 0x4d2c6dfcu, 0x53380d13u,
+            0x650a7354u, 0x766a0abbu, 0x81c2c92eu, 0x92722c85u, 0xa2bfe8a1u, 0xa81a664bu, 0xc24b8b70u, 0xc76c51a3u, 0xd192e819u, 0xd6990624u, 0xf40e3585u, 0x106aa070u,
+            0x19a4c116u, 0x1e376c08u, 0x2748774cu, 0x34b0bcb5u, 0x391c0cb3u, 0x4ed8aa4au, 0x5b9cca4fu, 0x682e6ff3u, 0x748f82eeu, 0x78a5636fu, 0x84c87814u, 0x8cc70208u,
+            0x90befffau, 0xa4506cebu, 0xbef9a3f7u, 0xc67178f2u};
+        uint32_t w[64];
+        for (int i = 0; i < 16; i++) w[i] = rd_u32be(p + 4 * i);
+        for (int i = 16; i < 64; i++) {
+            uint32_t s0 = ror(w[i - 15], 7) ^ ror(w[i - 15], 18) ^ (w[i - 15] >> 3), s1 = ror(w[i - 2], 17) ^ ror(w[i - 2], 19) ^ (w[i - 2] >> 10);
+            w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+        }
+        uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+        for (int i = 0; i < 64; i++) {
+            uint32_t t1 = hh + (ror(e, 6) ^ ror(e, 11) ^ ror(e, 25)) + ((e & f) ^ (~e & g)) + K[i] + w[i];
+            uint32_t t2 = (ror(a, 2) ^ ror(a, 13) ^ ror(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
+            hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+        }
+        h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+    }
+    void update(const uint8_t *p, size_t n) {
+        total += n;
+        if (fill) { size_t k = 64 - fill < n ? 64 - fill : n; memcpy(blk + fill, p, k); fill += k; p += k; n -= k; if (fill == 64) { block(blk); fill = 0; } }
+        for (; n >= 64; p += 64, n -= 64) block(p);
+        if (n) { memcpy(blk, p, n); fill = n; }
+    }
+    void finish(uint8_t out[32]) {
+        uint64_t bits = total * 8;
+        uint8_t pad[72] = {0x80};
+        size_t k = (fill < 56 ? 56 : 120) - fill;
+        update(pad, k);
+        uint8_t lenb[8];
+        for (int i = 0; i < 8; i++) lenb[i] = (uint8_t)(bits >> (56 - 8 * i));
+        update(lenb, 8);
+        for (int i = 0; i < 8; i++) wr_u32be(out + 4 * i, h[i]);
+    }
+};
+struct CacheHeader {
+    char magic[8];              // "ZKB2CRS1"
+    uint64_t pk_len;
+    uint8_t sha[32];
+    uint64_t cnt[6];
+    uint64_t g1_points, g2_points;
+};
+}  // namespace
+extern "C" int zk_params_load_cached(zk_ctx *ctx, const uint8_t *buf, size_t len, const char *cache_path, int *cache_hit, zk_params **out) {
+    if (!ctx || !buf || !out || !cache_path) { zk_set_error("zk_params_load_cached: NULL argument"); return ZK_ERR_INVALID; }
+    if (cache_hit) *cache_hit = 0;
+    ZK_TRY(zk_use_device(ctx));
+    size_t voff[6], vcnt[6];
+    ZK_TRY(params_walk(buf, len, voff, vcnt));
+    CrsLayout L(vcnt);
+    CacheHeader want;
+    memset(&want, 0, sizeof(want));
+    memcpy(want.magic, "ZKB2CRS1", 8);
+    want.pk_len = len;
+    { Sha256 s; s.update(buf, len); s.finish(want.sha); }
+    for (int k = 0; k < 6; k++) want.cnt[k] = vcnt[k];
+    want.g1_points = L.g1_total; want.g2_points = L.g2_total;
+    const size_t b1 = L.g1_total * sizeof(G1Affine), b2 = L.g2_total * sizeof(G2Affine);
+    if (FILE *f = fopen(cache_path, "rb")) {
+        CacheHeader got;
+        std::vector<uint8_t> body;
+        bool ok = fread(&got, sizeof(got), 1, f) == 1 && memcmp(&got, &want, sizeof(got)) == 0;
+        if (ok) { body.resize(b1 + b2); ok = fread(body.data(), 1, b1 + b2, f) == b1 + b2 && fgetc(f) == EOF; }
+        fclose(f);
+        if (ok) {
+            ZK_TRY(ctx->stage_b.reserve(b1 + 8 * sizeof(G1Affine)));
+            ZK_TRY(ctx->stage_c.reserve(b2 + 8 * sizeof(G2Affine)));
+            ZK_CUDA(cudaMemcpyAsync(ctx->stage_b.p, body.data(), b1, cudaMemcpyHostToDevice, ctx->stream));
+            ZK_CUDA(cudaMemcpyAsync(ctx->stage_c.p, body.data() + b1, b2, cudaMemcpyHostToDevice, ctx->stream));
+            ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (cache_hit) *cache_hit = 1;
+            return params_from_device(ctx, L, ctx->stage_b.as<G1Affine>(), ctx->stage_c.as<G2Affine>(), out);
+        }
+    }
+    // miss (absent, other key, truncated): the full checked load, then the cache is (re)written
+    ZK_TRY(params_decode(ctx, buf, len, 1, voff, L));
+    std::vector<uint8_t> body(b1 + b2);
+    ZK_CUDA(cudaMemcpyAsync(body.data(), ctx->stage_b.p, b1, cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(cudaMemcpyAsync(body.data() + b1, ctx->stage_c.p, b2, cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(cudaStreamSynchronize(ctx->stream));
+    ZK_TRY(params_from_device(ctx, L, ctx->stage_b.as<G1Affine>(), ctx->stage_c.as<G2Affine>(), out));
+    std::string tmp = std::string(cache_path) + ".tmp";
+    if (FILE *f = fopen(tmp.c_str(), "wb")) {           // a cache that cannot be written is not an error of the load
+        bool ok = fwrite(&want, sizeof(want), 1, f) == 1 && fwrite(body.data(), 1, body.size(), f) == body.size();
+        ok = (fclose(f) == 0) && ok;
+        if (ok) rename(tmp.c_str(), cache_path); else remove(tmp.c_str());
+    }
     return ZK_OK;
 }
 
@@ -143,6 +334,7 @@ __global__ void __launch_bounds__(SCALE_T) k_scale_points(const G1XYZZ *__restri
     const uint32_t *k = terms + (b * 4 + (j ? 1 : 2)) * 8;                       // j=0: s, j=1: r
     int top = -1;
     for (int i = 7; i >= 0 && top < 0; i--) if (k[i]) top = 32 * i + 31 - __clz(k[i]);
+    if (top > 254) top = 254;          // a non-canonical r / s (>= 2^255) is reported through the error flag by k_blinding_terms; stay inside pw[]
     if (t == 0) {
         G1XYZZ d = j ? gb1[b] : ga[b];
         pw[0] = d;
@@ -174,6 +366,30 @@ __global__ void __launch_bounds__(64) k_finish_proofs(const G1XYZZ *__restrict__
     zkcodec::encode_point(o + 48, gb[b].to_affine(), true);
     zkcodec::encode_point(o + 144, c.to_affine(), true);
 }
+}  // namespace
+
+// The four inter-lane events of one prove call.  If the call fails after the auxiliary lanes have been started, the lanes are
+// drained (their kernels still read g_scal2 / g_scal3, which the next call would overwrite) and their error flags cleared,
+// keeping the error text of the failure that caused the exit.
+namespace {
+struct LaneEvents {
+    cudaEvent_t b = nullptr, g2 = nullptr, a = nullptr, l3 = nullptr;
+    zk_ctx *lane2 = nullptr, *lane3 = nullptr;
+    bool lanes_started = false, completed = false;
+    int create() {
+        for (cudaEvent_t *e : {&b, &g2, &a, &l3}) ZK_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        return ZK_OK;
+    }
+    ~LaneEvents() {
+        if (lanes_started && !completed) {
+            std::string keep = zk_last_error();
+            cudaStreamSynchronize(lane2->stream); cudaStreamSynchronize(lane3->stream);
+            zk_check_err_flag(lane2); zk_check_err_flag(lane3);
+            zk_set_error("%s", keep.c_str());
+        }
+        for (cudaEvent_t e : {b, g2, a, l3}) if (e) cudaEventDestroy(e);
+    }
+};
 }  // namespace
 
 // batches larger than PROVE_CHUNK are processed in slices (device workspace and the 31-bit MSM entry index bound the slice)
@@ -253,37 +469,30 @@ static int prove_impl(zk_ctx *ctx, const zk_params *p, size_t batch,
     if (bi_idx.size()) k_gather32<<<dim3((unsigned)((bi_idx.size() + 255) / 256), (unsigned)batch), 256, 0, st>>>(d_in, n_in, d_biidx, bi_idx.size(), scal2, nB, 0);
     if (ba_idx.size()) k_gather32<<<dim3((unsigned)((ba_idx.size() + 255) / 256), (unsigned)batch), 256, 0, st>>>(d_aux, n_aux, d_baidx, ba_idx.size(), scal2, nB, bi_idx.size());
     k_put_terms<<<(unsigned)((batch + 63) / 64), 64, 0, st>>>((const uint4 *)d_terms, 0, 2, 2, scal2, nB, nB - 2, batch);
-    cudaEvent_t ev_b = nullptr, ev_g2 = nullptr;
-    ZK_CUDA(cudaEventCreateWithFlags(&ev_b, cudaEventDisableTiming));
-    ZK_CUDA(cudaEventCreateWithFlags(&ev_g2, cudaEventDisableTiming));
+    LaneEvents ev;
+    ev.lane2 = lane2; ev.lane3 = lane3;
+    ZK_TRY(ev.create());
+    cudaEvent_t ev_b = ev.b, ev_g2 = ev.g2, ev_a = ev.a, ev_l3 = ev.l3;
     ZK_CUDA(cudaEventRecord(ev_b, st));
     ZK_CUDA(cudaStreamWaitEvent(lane2->stream, ev_b, 0));
-    int rc2 = zk_msm_run(lane2, p->b2, scal2, nB, batch);
-    if (rc2 == ZK_OK) {
-        cudaMemcpyAsync(d_gb, lane2->result.p, batch * sizeof(G2XYZZ), cudaMemcpyDeviceToDevice, lane2->stream);
-        cudaEventRecord(ev_g2, lane2->stream);
-    } else { cudaEventDestroy(ev_b); cudaEventDestroy(ev_g2); return rc2; }
+    ev.lanes_started = true;
+    ZK_TRY(zk_msm_run(lane2, p->b2, scal2, nB, batch));
+    ZK_CUDA(cudaMemcpyAsync(d_gb, lane2->result.p, batch * sizeof(G2XYZZ), cudaMemcpyDeviceToDevice, lane2->stream));
+    ZK_CUDA(cudaEventRecord(ev_g2, lane2->stream));
     // third lane: g_a = MSM(a', inputs ++ aux|A ++ [1, r]) and g_b1 = MSM(b_g1', B scalars) need only the assignment too
     uint4 *scal3 = ctx->g_scal3.as<uint4>();
     ZK_CUDA(cudaMemcpy2DAsync(scal3, nA * 32, d_in, n_in * 32, n_in * 32, batch, cudaMemcpyDeviceToDevice, st));
     if (a_idx.size()) k_gather32<<<dim3((unsigned)((a_idx.size() + 255) / 256), (unsigned)batch), 256, 0, st>>>(d_aux, n_aux, d_aidx, a_idx.size(), scal3, nA, n_in);
     k_put_terms<<<(unsigned)((batch + 63) / 64), 64, 0, st>>>((const uint4 *)d_terms, 0, 1, 2, scal3, nA, nA - 2, batch);
-    cudaEvent_t ev_a = nullptr, ev_l3 = nullptr;
-    ZK_CUDA(cudaEventCreateWithFlags(&ev_a, cudaEventDisableTiming));
-    ZK_CUDA(cudaEventCreateWithFlags(&ev_l3, cudaEventDisableTiming));
     ZK_CUDA(cudaEventRecord(ev_a, st));
     ZK_CUDA(cudaStreamWaitEvent(lane3->stream, ev_a, 0));
-    int rc3 = zk_msm_run(lane3, p->a, scal3, nA, batch);
-    if (rc3 == ZK_OK) {
-        cudaMemcpyAsync(d_ga, lane3->result.p, batch * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, lane3->stream);
-        rc3 = zk_msm_run(lane3, p->b1, scal2, nB, batch);
-    }
-    if (rc3 == ZK_OK) {
-        cudaMemcpyAsync(d_gb1, lane3->result.p, batch * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, lane3->stream);
-        // s*g_a and r*g_b1 need only this lane's results, so they run here, under the NTT -> H -> L chain of the first lane
-        k_scale_points<<<(unsigned)(2 * batch), SCALE_T, 0, lane3->stream>>>(d_ga, d_gb1, (const uint32_t *)d_terms, batch, d_T);
-        cudaEventRecord(ev_l3, lane3->stream);
-    } else { cudaEventDestroy(ev_b); cudaEventDestroy(ev_g2); cudaEventDestroy(ev_a); cudaEventDestroy(ev_l3); return rc3; }
+    ZK_TRY(zk_msm_run(lane3, p->a, scal3, nA, batch));
+    ZK_CUDA(cudaMemcpyAsync(d_ga, lane3->result.p, batch * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, lane3->stream));
+    ZK_TRY(zk_msm_run(lane3, p->b1, scal2, nB, batch));
+    ZK_CUDA(cudaMemcpyAsync(d_gb1, lane3->result.p, batch * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, lane3->stream));
+    // s*g_a and r*g_b1 need only this lane's results, so they run here, under the NTT -> H -> L chain of the first lane
+    k_scale_points<<<(unsigned)(2 * batch), SCALE_T, 0, lane3->stream>>>(d_ga, d_gb1, (const uint32_t *)d_terms, batch, d_T);
+    ZK_CUDA(cudaEventRecord(ev_l3, lane3->stream));
     if (r1cs) {
         ZK_TRY(ctx->g_b.reserve(batch * (n_in + n_aux) * 32));       // z in Montgomery form
         ZK_TRY(zk_fr_witness_to_mont(ctx, d_in, n_in, d_aux, n_aux, batch, ctx->g_b.p));
@@ -317,8 +526,10 @@ static int prove_impl(zk_ctx *ctx, const zk_params *p, size_t batch,
     ZK_CUDA(cudaGetLastError());
     ZK_CUDA(cudaMemcpyAsync(proofs_out, d_proofs, batch * 192, cudaMemcpyDeviceToHost, st));
     int rc = zk_check_err_flag(ctx);    // synchronises this lane (which has joined the second); reports non-canonical scalars
+    std::string msg = rc ? zk_last_error() : "";
     int rcb = zk_check_err_flag(lane2), rcc = zk_check_err_flag(lane3);
-    cudaEventDestroy(ev_b); cudaEventDestroy(ev_g2); cudaEventDestroy(ev_a); cudaEventDestroy(ev_l3);
+    if (rc) zk_set_error("%s", msg.c_str());
+    ev.completed = true;                // every lane has been synchronised and its error flag read
     return rc ? rc : (rcb ? rcb : rcc);
 }
 

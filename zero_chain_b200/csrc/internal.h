@@ -38,6 +38,9 @@ struct DevBuf {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// one cached set of NTT twiddle tables (ntt.cu)
+struct NttSlot { unsigned log_n = 0; bool valid = false; uint64_t last_use = 0; DevBuf w, g, gi, consts; };
+
 struct zk_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -50,8 +53,11 @@ struct zk_ctx {
     bool len_hist_zeroed = false;
     // generic staging
     DevBuf stage_a, stage_b, stage_c;
-    // NTT workspace
-    DevBuf ntt_tw, ntt_tmp;
+    // NTT workspace + twiddle tables (per context: ordered on this context's stream, freed with it)
+    DevBuf ntt_tmp;
+    NttSlot ntt_slots[4];
+    uint64_t ntt_clock = 0;
+    bool ntt_attr_done = false;
     // groth16 workspace
     DevBuf g_a, g_b, g_c, g_h, g_scal, g_misc;
     // verifier workspace (pairing.cu)

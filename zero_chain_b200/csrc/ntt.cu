@@ -201,24 +201,26 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_rows(const Fr *__restrict__
 
 }  // namespace
 
-struct NttTables { unsigned log_n = 0; bool valid = false; DevBuf w, g, gi, consts; };
-static NttTables g_tables[8][6];   // [device][slot]
-
-static int get_tables(zk_ctx *ctx, unsigned log_n, NttTables **out) {
-    if (ctx->device >= 8) { zk_set_error("device index too large"); return ZK_ERR_INVALID; }
-    NttTables *slots = g_tables[ctx->device], *free_slot = nullptr;
-    for (int i = 0; i < 6; i++) {
-        if (slots[i].valid && slots[i].log_n == log_n) { *out = &slots[i]; return ZK_OK; }
-        if (!slots[i].valid && !free_slot) free_slot = &slots[i];
+// Twiddle tables (w^i, g^i, g^-i / m) live in the CONTEXT that uses them (internal.h: zk_ctx::ntt_slots): a context is single-threaded
+// and owns one stream, so building a table, rebuilding a slot for another size and reading it are all ordered on that stream —
+// no cross-stream or cross-thread hazards, nothing process-global, and zk_ctx_destroy frees them.  Least-recently-used slot is recycled.
+static int get_tables(zk_ctx *ctx, unsigned log_n, NttSlot **out) {
+    NttSlot *victim = nullptr;
+    ctx->ntt_clock++;
+    for (NttSlot &sl : ctx->ntt_slots)
+        if (sl.valid && sl.log_n == log_n) { sl.last_use = ctx->ntt_clock; *out = &sl; return ZK_OK; }
+    for (NttSlot &sl : ctx->ntt_slots) {            // an empty slot if there is one, else the least recently used
+        if (!sl.valid) { victim = &sl; break; }
+        if (!victim || sl.last_use < victim->last_use) victim = &sl;
     }
-    if (!free_slot) free_slot = &slots[log_n % 6];
     size_t n = (size_t)1 << log_n;
-    ZK_TRY(free_slot->w.reserve(n * 32)); ZK_TRY(free_slot->g.reserve(n * 32)); ZK_TRY(free_slot->gi.reserve(n * 32)); ZK_TRY(free_slot->consts.reserve(64));
-    k_ntt_tables<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(free_slot->w.as<Fr>(), free_slot->g.as<Fr>(), free_slot->gi.as<Fr>(),
-                                                                       free_slot->consts.as<Fr>(), log_n);
+    victim->valid = false;
+    ZK_TRY(victim->w.reserve(n * 32)); ZK_TRY(victim->g.reserve(n * 32)); ZK_TRY(victim->gi.reserve(n * 32)); ZK_TRY(victim->consts.reserve(64));
+    k_ntt_tables<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(victim->w.as<Fr>(), victim->g.as<Fr>(), victim->gi.as<Fr>(),
+                                                                       victim->consts.as<Fr>(), log_n);
     ZK_CUDA(cudaGetLastError());
-    free_slot->log_n = log_n; free_slot->valid = true;
-    *out = free_slot;
+    victim->log_n = log_n; victim->valid = true; victim->last_use = ctx->ntt_clock;
+    *out = victim;
     return ZK_OK;
 }
 
@@ -234,17 +236,16 @@ int zk_ntt_run(zk_ctx *ctx, void *d_data, unsigned log_n, int mode, size_t batch
     if (log_n > 2 * MAX_TILE_LOG && batch != 1) { zk_set_error("batched NTTs above 2^22 are not supported"); return ZK_ERR_INVALID; }
     ZK_TRY(zk_use_device(ctx));
     if (log_n == 0) return ZK_OK;     // size-1 transform is the identity (m^-1 = 1)
-    NttTables *t;
+    NttSlot *t;
     ZK_TRY(get_tables(ctx, log_n, &t));
     const size_t n = (size_t)1 << log_n;
     const int inverse = (mode == ZK_NTT_IFFT || mode == ZK_NTT_ICOSET_FFT);
     const int coset_in = (mode == ZK_NTT_COSET_FFT);
     const int post = mode == ZK_NTT_IFFT ? 1 : (mode == ZK_NTT_ICOSET_FFT ? 2 : 0);
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (!ctx->ntt_attr_done) {         // the attribute is per device; a context is bound to one device
         ZK_CUDA(cudaFuncSetAttribute(k_ntt_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << MAX_TILE_LOG));
         ZK_CUDA(cudaFuncSetAttribute(k_ntt_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << MAX_TILE_LOG));
-        attr_done = true;
+        ctx->ntt_attr_done = true;
     }
     Fr *data = (Fr *)d_data;
     const Fr *W = t->w.as<Fr>(), *G = t->g.as<Fr>(), *GI = t->gi.as<Fr>(), *consts = t->consts.as<Fr>();
@@ -404,7 +405,7 @@ int zk_fr_load_evals(zk_ctx *ctx, const void *d_src, size_t n_c, unsigned log_m,
     return ZK_OK;
 }
 int zk_fr_quotient(zk_ctx *ctx, const void *d_abc, unsigned log_m, size_t batch, void *d_h) {
-    NttTables *t;
+    NttSlot *t;
     ZK_TRY(get_tables(ctx, log_m, &t));
     size_t m = (size_t)1 << log_m;
     k_quotient<<<dim3((unsigned)((m + 255) / 256), (unsigned)batch), 256, 0, ctx->stream>>>((const Fr *)d_abc, log_m, t->consts.as<Fr>(), (Fr *)d_h);

@@ -318,8 +318,7 @@ extern "C" int zk_groth16_verify_batch_device(zk_ctx *ctx, const zk_pvk *k, size
     if (!n) return ZK_OK;
     ZK_TRY(zk_use_device(ctx));
     if (k->device != ctx->device) { zk_set_error("prepared key lives on device %d, context on %d", k->device, ctx->device); return ZK_ERR_INVALID; }
-    size_t chunk = VERIFY_CHUNK;
-    if (const char *e = getenv("ZK_VERIFY_CHUNK")) { long v = atol(e); if (v > 0) chunk = (size_t)v; }     // test hook
+    const size_t chunk = VERIFY_CHUNK;
     if (n > chunk) {                   // bound the workspace (19.6 KB of B coefficients per proof): slices run back to back on the stream
         for (size_t o = 0; o < n; o += chunk) {
             size_t m = n - o < chunk ? n - o : chunk;

@@ -216,6 +216,31 @@ class Parameters:
         _ck(_lib.lib().zk_params_counts(h, _p(cnt)))
         return Parameters(ctx, h, [int(x) for x in cnt])
 
+    @staticmethod
+    def read_cached(ctx: Context, buf: bytes, cache_path: str) -> "Parameters":
+        """Parameters::read(buf, true) through the decoded-CRS cache on disk (zk_params_load_cached); `.cache_hit` tells which
+        path ran.  The reference re-reads and re-checks the whole proving key on every start (crypto_components.rs:320-328)."""
+        b = np.frombuffer(buf, np.uint8)
+        h, hit = C.c_void_p(), C.c_int(0)
+        _ck(_lib.lib().zk_params_load_cached(ctx._h, _p(b), len(buf), cache_path.encode(), C.byref(hit), C.byref(h)))
+        cnt = np.zeros(6, np.uint64)
+        _ck(_lib.lib().zk_params_counts(h, _p(cnt)))
+        prm = Parameters(ctx, h, [int(x) for x in cnt])
+        prm.cache_hit = bool(hit.value)
+        return prm
+
+    def write(self) -> bytes:
+        """Parameters::write (core/proofs/src/confidential.rs:83): the resident CRS as the exact byte stream `read` consumes."""
+        out = np.zeros(int(_lib.lib().zk_params_size(self._h)), np.uint8)
+        _ck(_lib.lib().zk_params_write(self.ctx._h, self._h, _p(out)))
+        return out.tobytes()
+
+    def vk_bytes(self) -> bytes:
+        """VerifyingKey::write of `params.vk` (core/proofs/src/setup.rs:31): the head of the Parameters stream."""
+        out = np.zeros(int(_lib.lib().zk_params_vk_size(self._h)), np.uint8)
+        _ck(_lib.lib().zk_params_write_vk(self.ctx._h, self._h, _p(out)))
+        return out.tobytes()
+
     def free(self):
         if self._h:
             _lib.lib().zk_params_free(self._h)
