@@ -100,9 +100,263 @@ class ClockSampler:
         return out
 
 
+R_MODULUS = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+
+
+def dot_mod_r(s, b):
+    """sum_i s_i * b_i mod r for two (n,4) uint64 limb arrays, exact, with numpy only (no curve code, nothing shared with
+    the library or the oracle): 16-bit chunks, so that every partial dot product stays below 2^64 for n <= 2^24."""
+    s = np.ascontiguousarray(s, np.uint64).reshape(-1, 4)
+    b = np.ascontiguousarray(b, np.uint64).reshape(-1, 4)
+    assert s.shape == b.shape and s.shape[0] <= (1 << 24)
+    s16, b16 = s.view(np.uint16).reshape(-1, 16), b.view(np.uint16).reshape(-1, 16)
+    bcols = [(k, b16[:, k].astype(np.uint64)) for k in range(16) if b16[:, k].any()]
+    total = 0
+    for j in range(16):
+        sj = s16[:, j].astype(np.uint64)
+        for k, bk in bcols:
+            total += int(np.dot(sj, bk)) << (16 * (j + k))
+    return total % R_MODULUS
+
+
+def closed_form_g1(k):
+    """Uncompressed encoding of k * G1 by the big-integer affine reference (oracle/pyref.py — used as the checker only)."""
+    from oracle import pyref as pr
+    return pr.g1_uncompressed(pr.ec_mul(pr.FQ, pr.G1_GEN, k % R_MODULUS))
+
+
+# ---- witness factory for the proofs/sec leg: runs in worker PROCESSES (spawn), numpy / big-int only ----
+_WK = {}
+
+
+def _wk_init(crs_light):
+    _WK["crs"] = crs_light
+
+
+def _wk_witness(k):
+    """Witness k of the synthetic confidential_transfer-shaped circuit: evaluations, assignment, (r, s) and the proof the
+    trapdoor algebra predicts for them (closed form, oracle/pyref.py big-integer curve arithmetic: the checker)."""
+    from oracle import pyref as pr
+    from zero_chain_b200 import synthetic as sy
+    crs = _WK["crs"]
+    r = crs.r1cs
+    z = sy.make_witness(r, 100 + k)
+    a, b, c = sy.evaluate(r, z)
+    rng = sy.SplitMix64(4242 + 7919 * k)
+    rr, ss = rng.fr(), rng.fr()
+    A, B, C = sy.expected_proof_scalars(crs, z, rr, ss)
+    want = pr.proof_bytes(pr.ec_mul(pr.FQ, pr.G1_GEN, A), pr.ec_mul(pr.FQ2, pr.G2_GEN, B), pr.ec_mul(pr.FQ, pr.G1_GEN, C))
+    arrs = [sy.ints_to_limbs(v) for v in (a, b, c, z[:r.n_inputs], z[r.n_inputs:])]
+    return k, arrs, rr, ss, want
+
+
+def make_witnesses(crs, count, procs):
+    """`count` DISTINCT witnesses with distinct (r, s) and their closed-form proofs, generated in parallel on the host."""
+    import dataclasses
+    import multiprocessing as mp
+    light = dataclasses.replace(crs, params_bytes=b"")
+    procs = max(1, min(procs, count))
+    if procs == 1:
+        _wk_init(light)
+        res = [_wk_witness(k) for k in range(count)]
+    else:
+        with mp.get_context("spawn").Pool(procs, initializer=_wk_init, initargs=(light,)) as pool:
+            res = pool.map(_wk_witness, range(count), chunksize=max(1, count // (4 * procs)))
+    res.sort(key=lambda t: t[0])
+    return res
+
+
 def make_scalars(n, rank, k):
     from zero_chain_b200 import synthetic as sy
     return sy.random_fr_limbs(n, 1000 + 97 * rank + k)
+
+
+class MsmJob:
+    """One sharded MSM workload on this rank: resident bases (+ window tables), N_SETS scalar vectors in HBM and in pinned
+    host memory, and the two ways of running a step (blocking calls / two futures in flight on two contexts)."""
+
+    def __init__(self, zk, torch, dist, ctxs, world, local, bases, h_sets, n):
+        self.zk, self.torch, self.dist, self.world, self.n, self.bases = zk, torch, dist, world, n, bases
+        self.ctx, self.ctx2 = ctxs
+        self.ns = len(h_sets)
+        self.dev = torch.device("cuda", local)
+        self.stream = torch.cuda.ExternalStream(self.ctx.stream, device=self.dev)
+        self.d_sets = [torch.from_numpy(h.view(np.int64)).cuda() for h in h_sets]
+        self.pinned = [torch.from_numpy(h.view(np.int64)).pin_memory() for h in h_sets]
+        psz = zk.partial_size(1)
+        self.d_part = torch.zeros(psz, dtype=torch.uint8, device="cuda")
+        self.d_all = torch.zeros(psz * world, dtype=torch.uint8, device="cuda")
+        self.d_stage = torch.empty_like(self.d_sets[0])
+        self.lanes = {}
+        if world > 1:      # per context: its partial, the gathered partials, a staging buffer for the e2e arm, torch views of its two streams
+            for c in ctxs:
+                self.lanes[id(c)] = dict(part=torch.zeros(psz, dtype=torch.uint8, device="cuda"), all=torch.zeros(psz * world, dtype=torch.uint8, device="cuda"),
+                                         stage=torch.empty_like(self.d_sets[0]), main=torch.cuda.ExternalStream(c.stream, device=self.dev),
+                                         tail=torch.cuda.ExternalStream(zk.tail_stream(c), device=self.dev))
+        torch.cuda.synchronize()
+
+    # ---- blocking calls ----
+    def step_device(self, k):
+        zk, d = self.zk, self.d_sets[k % self.ns]
+        if self.world == 1:
+            return zk.multiexp_device(self.bases, d.data_ptr(), self.n)
+        zk.multiexp_partial_device(self.bases, d.data_ptr(), self.n, self.d_part.data_ptr())
+        with self.torch.cuda.stream(self.stream):          # NCCL all-gather enqueued on the library's stream: no host sync needed
+            self.dist.all_gather_into_tensor(self.d_all, self.d_part)
+        return zk.points_fold(self.ctx, 1, self.d_all.data_ptr(), self.world)
+
+    def step_e2e(self, k):
+        zk, h = self.zk, self.pinned[k % self.ns]
+        if self.world == 1:
+            return zk.multiexp(self.bases, h.numpy().view(np.uint64).reshape(-1, 4))    # C-ABI call with a HOST buffer
+        with self.torch.cuda.stream(self.stream):
+            self.d_stage.copy_(h, non_blocking=True)
+        zk.multiexp_partial_device(self.bases, self.d_stage.data_ptr(), self.n, self.d_part.data_ptr())
+        with self.torch.cuda.stream(self.stream):
+            self.dist.all_gather_into_tensor(self.d_all, self.d_part)
+        return zk.points_fold(self.ctx, 1, self.d_all.data_ptr(), self.world)
+
+    # ---- futures ----
+    def _begin_multi(self, c, d_ptr):
+        L = self.lanes[id(c)]
+        self.zk.multiexp_partial_device_begin(c, self.bases, d_ptr, self.n, L["part"].data_ptr())
+        with self.torch.cuda.stream(L["tail"]):             # the all-gather is ordered after the partial on the context's tail stream
+            self.dist.all_gather_into_tensor(L["all"], L["part"])
+        self.zk.points_fold_begin(c, 1, L["all"].data_ptr(), self.world)
+
+    def begin_device(self, c, k):
+        if self.world == 1:
+            return self.zk.multiexp_device_begin(c, self.bases, self.d_sets[k % self.ns].data_ptr(), self.n)
+        self._begin_multi(c, self.d_sets[k % self.ns].data_ptr())
+
+    def begin_e2e(self, c, k):
+        if self.world == 1:
+            return self.zk.multiexp_begin(c, self.bases, self.pinned[k % self.ns].numpy().view(np.uint64).reshape(-1, 4))
+        L = self.lanes[id(c)]
+        with self.torch.cuda.stream(L["main"]):
+            L["stage"].copy_(self.pinned[k % self.ns], non_blocking=True)
+        self._begin_multi(c, L["stage"].data_ptr())
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def _max_over_ranks(self, ms):
+        if self.world == 1:
+            return ms
+        t = self.torch.tensor([ms], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, fn, steps, warmup):
+        torch = self.torch
+        for k in range(warmup):
+            fn(k)
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        last = None
+        for k in range(steps):
+            last = fn(warmup + k)
+        e1.record(self.stream)
+        self.barrier()
+        return self._max_over_ranks(e0.elapsed_time(e1)), last
+
+    def timed_pipelined(self, begin, steps, warmup, profile=False):
+        """successive MSMs are independent jobs and the reference's multiexp returns a future: two of them are kept in flight on
+        two contexts (zk_msm_begin / zk_msm_end), so the latency-bound tail of one MSM and the upload of the next scalars overlap
+        the accumulation of the other."""
+        torch, zk = self.torch, self.zk
+        ctxs = [self.ctx, self.ctx2]
+        res = {}
+
+        def run(k0, k1):
+            inflight = [None, None]
+            for k in range(k0, k1):
+                c = k % 2
+                if inflight[c] is not None:
+                    res[inflight[c]] = zk.multiexp_end(ctxs[c], self.bases)
+                begin(ctxs[c], k)
+                inflight[c] = k
+            for k in sorted(x for x in inflight if x is not None):
+                res[k] = zk.multiexp_end(ctxs[k % 2], self.bases)
+        run(0, warmup)
+        self.barrier()
+        if profile:
+            self.ctx.profile(True); self.ctx2.profile(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        run(warmup, warmup + steps)
+        e1.record(self.stream)                  # every MSM has been collected on the host, so this is after all of the work
+        self.barrier()
+        ms = self._max_over_ranks(e0.elapsed_time(e1))
+        prof = None
+        if profile:
+            a, b_ = self.ctx.profile_read(), self.ctx2.profile_read()
+            ca, cb = self.ctx.profile_counts(), self.ctx2.profile_counts()
+            prof = (a[0] + b_[0], a[1] + b_[1], ca[0] + cb[0])
+            self.ctx.profile(False); self.ctx2.profile(False)
+        return ms, res[warmup + steps - 1], prof
+
+    def close(self):
+        # ordered teardown: tensors that were used on the library's streams must be released before the streams are
+        # destroyed with the contexts (their allocator blocks record events on them when freed)
+        self.lanes.clear()
+        self.d_sets = self.pinned = self.d_stage = self.d_part = self.d_all = None
+        self.torch.cuda.synchronize()
+        self.torch.cuda.empty_cache()
+        self.bases.free()
+
+
+def gather_ints(dist, torch, world, value):
+    """all-gather one < 2^256 python integer per rank (as four 64-bit limbs over the process group)."""
+    if world == 1:
+        return [value]
+    limbs = np.array([(value >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(4)], dtype=np.uint64)
+    t = torch.from_numpy(limbs.view(np.int64)).cuda()
+    out = torch.zeros(4 * world, dtype=torch.int64, device="cuda")
+    dist.all_gather_into_tensor(out, t)
+    rows = out.cpu().numpy().view(np.uint64).reshape(world, 4)
+    return [sum(int(x) << (64 * j) for j, x in enumerate(r)) for r in rows]
+
+
+def strong_scaling_leg(zk, sy, torch, dist, ctxs, world, rank, local, log_total, steps):
+    """BASELINE.json configs[4] / SURVEY.md §8(d) C5: ONE G1 MSM of 2^log_total terms, bases (g+1)*G over the GLOBAL index g,
+    sharded by contiguous range over the ranks (2^24 over 8 GPUs = 2^21 per GPU), partial sums all-gathered over NCCL and folded.
+    Fixed total work as N grows = strong scaling.  The folded result is checked against the closed form (sum s_g (g+1) mod r) * G."""
+    total = 1 << log_total
+    n = total // world
+    g0 = rank * n
+    t0 = time.time()
+    idx = np.zeros((n, 4), np.uint64)
+    idx[:, 0] = np.arange(g0 + 1, g0 + n + 1, dtype=np.uint64)
+    bases_limbs = zk.scalar_mul_many(ctxs[0], 1, zk.G1_GENERATOR, idx)
+    bases = zk.Bases(ctxs[0], 1, bases_limbs, precompute=True)
+    del bases_limbs
+    n_sets = 2
+    h_sets = [sy.random_fr_limbs(n, 5000 + 31 * rank + k) for k in range(n_sets)]
+    job = MsmJob(zk, torch, dist, ctxs, world, local, bases, h_sets, n)
+    setup_s = time.time() - t0
+    W = 2
+    ms_p, res_p, _ = job.timed_pipelined(job.begin_device, steps, W)
+    ms_b, res_b = job.timed(job.step_device, steps, W)
+    last = (W + steps - 1) % n_sets
+    parts = gather_ints(dist, torch, world, dot_mod_r(h_sets[last], idx))
+    out = None
+    if rank == 0:
+        want = closed_form_g1(sum(parts))
+        ok = (res_p == want) and (res_b == want)
+        out = {"metric": "g1_msm_mops_2^%d_total" % log_total, "scaling": "strong", "total_terms": total, "terms_per_gpu": n, "n_gpus": world,
+               "value": total * steps / (ms_p * 1e-3) / 1e6, "unit": "Mop/s", "ms_per_step": ms_p / steps, "steps": steps, "warmup": W,
+               "blocking_ms_per_step": ms_b / steps, "blocking_mops": total * steps / (ms_b * 1e-3) / 1e6,
+               "window_bits": bases.window_bits, "bases": "(g+1)*G over the global index g (SURVEY 8d C5)", "setup_s_untimed": round(setup_s, 2),
+               "matches_closed_form": bool(ok),
+               "check": "folded result == (sum_g s_g (g+1) mod r) * G; per-rank dot products in numpy, scalar multiple by oracle/pyref.py"}
+        if not ok:
+            raise SystemExit("PARITY FAILURE: sharded 2^%d MSM differs from the closed form" % log_total)
+    job.close()
+    return out
 
 
 def run_ours(args):
@@ -134,175 +388,78 @@ def run_ours(args):
             os.dup2(saved, 1)
             os.close(saved)
     n = 1 << args.log_n
-    ctx = zk.Context(local)
-    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+    ctx, ctx2 = zk.Context(local), zk.Context(local)
 
     # ---- setup (untimed): this rank's shard of the bases, generated on the device, + window tables ----
     t0 = time.time()
     base_scalars = sy.random_fr_limbs(n, 7 + rank)
-    bases_limbs = zk.scalar_mul_many(ctx, 1, zk.G1_GENERATOR, base_scalars)      # uniform random subgroup points
+    bases_limbs = zk.scalar_mul_many(ctx, 1, zk.G1_GENERATOR, base_scalars)      # uniform random subgroup points b_i * G
     bases = zk.Bases(ctx, 1, bases_limbs, window_bits=args.window_bits, precompute=True)
     setup_s = time.time() - t0
     h_sets = [make_scalars(n, rank, k) for k in range(N_SETS)]
-    d_sets = [torch.from_numpy(h.view(np.int64)).cuda() for h in h_sets]
-    pinned = [torch.from_numpy(h.view(np.int64)).pin_memory() for h in h_sets]
-    psz = zk.partial_size(1)
-    d_part = torch.zeros(psz, dtype=torch.uint8, device="cuda")
-    d_all = torch.zeros(psz * world, dtype=torch.uint8, device="cuda")
-    torch.cuda.synchronize()
-
-    def step_device(k):
-        d = d_sets[k % N_SETS]
-        if world == 1:
-            return zk.multiexp_device(bases, d.data_ptr(), n)
-        zk.multiexp_partial_device(bases, d.data_ptr(), n, d_part.data_ptr())
-        with torch.cuda.stream(stream):                 # NCCL all-gather enqueued on the library's stream: no host sync needed
-            dist.all_gather_into_tensor(d_all, d_part)
-        return zk.points_fold(ctx, 1, d_all.data_ptr(), world)
-
-    d_stage = torch.empty_like(d_sets[0])
-
-    def step_e2e(k):
-        h = pinned[k % N_SETS]
-        if world == 1:
-            return zk.multiexp(bases, h.numpy().view(np.uint64).reshape(-1, 4))    # C-ABI call with a HOST buffer
-        with torch.cuda.stream(stream):
-            d_stage.copy_(h, non_blocking=True)
-        zk.multiexp_partial_device(bases, d_stage.data_ptr(), n, d_part.data_ptr())
-        with torch.cuda.stream(stream):
-            dist.all_gather_into_tensor(d_all, d_part)
-        return zk.points_fold(ctx, 1, d_all.data_ptr(), world)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps, warmup, profile=False):
-        for k in range(warmup):
-            fn(k)
-        barrier()
-        if profile:
-            ctx.profile(True)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        last = None
-        for k in range(steps):
-            last = fn(warmup + k)
-        e1.record(stream)
-        barrier()
-        ms = e0.elapsed_time(e1)
-        prof = ctx.profile_read() if profile else None
-        if profile:
-            ctx.profile(False)
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), last, prof
-
-    # world == 1: successive MSMs are independent jobs, and the reference's multiexp returns a future — the timed loop keeps two
-    # of them in flight on two contexts (zk_msm_begin / zk_msm_end), so the latency-bound tail of one MSM and the upload of the
-    # next scalars overlap the accumulation of the other.  The blocking single-call numbers are reported beside it.
-    ctx2 = zk.Context(local)
-
-    def timed_pipelined(begin, steps, warmup, profile=False):
-        ctxs = [ctx, ctx2]
-        res = {}
-
-        def run(k0, k1):
-            inflight = [None, None]
-            for k in range(k0, k1):
-                c = k % 2
-                if inflight[c] is not None:
-                    res[inflight[c]] = zk.multiexp_end(ctxs[c], bases)
-                begin(ctxs[c], k)
-                inflight[c] = k
-            for k in sorted(x for x in inflight if x is not None):
-                res[k] = zk.multiexp_end(ctxs[k % 2], bases)
-        run(0, warmup)
-        barrier()
-        if profile:
-            ctx.profile(True); ctx2.profile(True)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        run(warmup, warmup + steps)
-        e1.record(stream)                      # every MSM has been collected on the host, so this is after all of the work
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        prof = None
-        if profile:
-            a, b_ = ctx.profile_read(), ctx2.profile_read()
-            prof = (a[0] + b_[0], a[1] + b_[1])
-            ctx.profile(False); ctx2.profile(False)
-        return ms, res[warmup + steps - 1], prof
-
-    if world == 1:
-        begin_device = lambda c, k: zk.multiexp_device_begin(c, bases, d_sets[k % N_SETS].data_ptr(), n)
-        begin_e2e = lambda c, k: zk.multiexp_begin(c, bases, pinned[k % N_SETS].numpy().view(np.uint64).reshape(-1, 4))
-    else:
-        # per context: its partial, the gathered partials, a staging buffer for the e2e arm, and torch views of its two streams
-        lanes = {}
-        for c in (ctx, ctx2):
-            lanes[id(c)] = dict(part=torch.zeros(psz, dtype=torch.uint8, device="cuda"), all=torch.zeros(psz * world, dtype=torch.uint8, device="cuda"),
-                                stage=torch.empty_like(d_sets[0]), main=torch.cuda.ExternalStream(c.stream, device=torch.device("cuda", local)),
-                                tail=torch.cuda.ExternalStream(zk.tail_stream(c), device=torch.device("cuda", local)))
-
-        def begin_multi(c, d_ptr):
-            L = lanes[id(c)]
-            zk.multiexp_partial_device_begin(c, bases, d_ptr, n, L["part"].data_ptr())
-            with torch.cuda.stream(L["tail"]):          # the all-gather is ordered after the partial on the context's tail stream
-                dist.all_gather_into_tensor(L["all"], L["part"])
-            zk.points_fold_begin(c, 1, L["all"].data_ptr(), world)
-
-        begin_device = lambda c, k: begin_multi(c, d_sets[k % N_SETS].data_ptr())
-
-        def begin_e2e(c, k):
-            L = lanes[id(c)]
-            with torch.cuda.stream(L["main"]):
-                L["stage"].copy_(pinned[k % N_SETS], non_blocking=True)
-            begin_multi(c, L["stage"].data_ptr())
+    job = MsmJob(zk, torch, dist, (ctx, ctx2), world, local, bases, h_sets, n)
 
     # modmul roofline calibrated live on this GPU (register-resident independent Fq products)
     modmul_peak, _ = zk.bench_modmul(ctx, zk.FIELD_FQ, 148 * 4, 256, 3000)
 
     sampler = ClockSampler(local) if rank == 0 else None
-    W = max(4, args.warmup)            # the last timed step (W + steps - 1) picks the scalar set the CPU check uses
-    ms_dev, res_dev, prof = timed_pipelined(begin_device, args.steps, W, profile=True)
+    W = max(4, args.warmup)            # the last timed step (W + steps - 1) picks the scalar set the checks use
+    ms_dev, res_dev, prof = job.timed_pipelined(job.begin_device, args.steps, W, profile=True)
     clocks = sampler.stop() if sampler else None
-    ms_e2e, res_e2e, _ = timed_pipelined(begin_e2e, args.steps, W)
-    ms_b, res_b, _ = timed(step_device, args.steps, W)
-    ms_be, res_be, _ = timed(step_e2e, args.steps, W)
-    if not (res_b == res_dev and res_be == res_e2e):
-        raise SystemExit("PARITY FAILURE: pipelined and blocking MSM results differ")
+    ms_e2e, res_e2e, _ = job.timed_pipelined(job.begin_e2e, args.steps, W)
+    ms_b, res_b = job.timed(job.step_device, args.steps, W)
+    ms_be, res_be = job.timed(job.step_e2e, args.steps, W)
+    if not (res_b == res_dev == res_be == res_e2e):
+        raise SystemExit("PARITY FAILURE: pipelined / blocking / host-buffer MSM results differ")
     blocking = {"device_ms_per_step": ms_b / args.steps, "device_mops": n * world * args.steps / (ms_b * 1e-3) / 1e6,
                 "e2e_ms_per_step": ms_be / args.steps, "e2e_mops": n * world * args.steps / (ms_be * 1e-3) / 1e6,
                 "api": "zk_msm_device / zk_msm (N > 1: zk_msm_partial_device + all-gather + zk_points_fold), one call at a time"}
+    # fresh bases (bellman's multiexp takes the bases per call): no window tables, one bucket set per window + Horner tail
+    fresh = None
+    if world == 1 and args.secondary:
+        fb = zk.Bases(ctx, 1, bases_limbs, precompute=False)
+        fjob_step = lambda k: zk.multiexp_device(fb, job.d_sets[k % N_SETS].data_ptr(), n)
+        ms_f, res_f = job.timed(fjob_step, max(3, args.steps // 2), 2)
+        if res_f != zk.multiexp_device(bases, job.d_sets[(2 + max(3, args.steps // 2) - 1) % N_SETS].data_ptr(), n):
+            raise SystemExit("PARITY FAILURE: table-free MSM differs from the table MSM")
+        t1 = time.time(); tb = zk.Bases(ctx, 1, bases_limbs, window_bits=args.window_bits, precompute=True); table_s = time.time() - t1
+        tb.free()
+        fresh = {"device_ms_per_step": ms_f / max(3, args.steps // 2), "device_mops": n / (ms_f / max(3, args.steps // 2) * 1e-3) / 1e6, "window_bits": fb.window_bits,
+                 "api": "zk_bases_upload(precompute = 0) + zk_msm_device: per-call bases, %d-bit windows, one bucket set per window" % fb.window_bits,
+                 "table_build_s_incl_upload": table_s, "table_bytes": (255 // bases.window_bits + 1) * n * 96}
+        fb.free()
+    del bases_limbs
+
+    # ---- closed-form check at EVERY N: bases are b_i * G, so the folded result must be (sum_ranks sum_i s_i b_i mod r) * G ----
+    last_set = (W + args.steps - 1) % N_SETS
+    parts = gather_ints(dist, torch, world, dot_mod_r(h_sets[last_set], base_scalars))
+    closed_ok = None
+    if rank == 0:
+        closed_ok = closed_form_g1(sum(parts)) == res_dev
+        if not closed_ok:
+            raise SystemExit("PARITY FAILURE: MSM result differs from the closed form (sum s_i b_i) * G")
 
     total_terms = n * world
     value = total_terms * args.steps / (ms_dev * 1e-3) / 1e6
     e2e_value = total_terms * args.steps / (ms_e2e * 1e-3) / 1e6
     hbm_peak, hbm_how = peaks()
-    acc_ms, acc_launches = prof
+    acc_ms, acc_launches, acc_adds = prof
     acc_avg_s = acc_ms * 1e-3 / max(1, acc_launches)
     algo_modmul = ALGO_MODMUL_PER_TERM * n            # per launch: one launch processes one rank's n terms
+    exec_modmul = 10.0 * acc_adds / max(1, acc_launches)   # bucket additions counted on the device x 10 products (XYZZ mixed addition)
     roofline = {
         "kernel": "zkmsm::k_accumulate<Fq> (bucket accumulation)",
         "bound": "int32-modmul",                       # IMAD issue rate, not HBM, not tensor
+        # LEAD figure: products the kernel actually executes / time / calibrated peak = efficiency of the integer-multiply pipe
+        "executed_frac": exec_modmul / acc_avg_s / modmul_peak,
+        "executed_modmul_per_launch": exec_modmul,
         "achieved": algo_modmul / acc_avg_s, "peak": modmul_peak, "unit": "Fq-modmul/s",
         "frac": algo_modmul / acc_avg_s / modmul_peak,
         "peak_how": "zk_bench_modmul: register-resident independent Fq Montgomery products, measured in this run",
         "avg_launch_ms": acc_avg_s * 1e3, "launches": acc_launches, "share_of_step": acc_ms / ms_dev,
-        # the convention above counts 11 products x 16 windows per term; the kernel actually executes 10 products (XYZZ mixed
-        # addition) x W windows per term, so with W = 13 (20-bit windows) `frac` can exceed 1 — `executed_frac` is the pipe efficiency
-        "note": "frac uses SURVEY 8(d)'s fixed algorithmic count (176 products per term = 11 x 16 windows); the kernel executes "
-                "10 x %d per term (XYZZ mixed addition, %d-bit windows from precomputed tables), so frac can exceed 1 — executed_frac is "
-                "the pipe efficiency of the kernel as run" % (255 // bases.window_bits + 1, bases.window_bits),
-        "executed_modmul_per_launch": 10 * n * (255 // bases.window_bits + 1),
-        "executed_frac": 10 * n * (255 // bases.window_bits + 1) / acc_avg_s / modmul_peak,
+        "note": "frac uses SURVEY 8(d)'s FIXED algorithmic count (176 products per term = 11 x 16 windows) and can exceed 1 because "
+                "the kernel executes fewer (10 per mixed addition x %d table rows per term, %d-bit windows); executed_frac counts the "
+                "additions really performed (device counter) and is the pipe efficiency" % (255 // bases.window_bits + 1, bases.window_bits),
         "whole_msm_frac": ALGO_MODMUL_PER_TERM * total_terms * args.steps / (ms_dev * 1e-3) / (modmul_peak * world),
         "hbm": {"bound": "hbm", "achieved": ALGO_BYTES_PER_TERM * n / acc_avg_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": ALGO_BYTES_PER_TERM * n / acc_avg_s / 1e9 / hbm_peak, "peak_how": hbm_how},
@@ -316,28 +473,45 @@ def run_ours(args):
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import coracle as co
+        co.set_num_threads(os.cpu_count() or 1)
+        bl = co.g1_fixed_base(base_scalars)           # the same bases, made by the oracle's own fixed-base code
         t = time.time()
-        want = co.g1_msm(bases_limbs, h_sets[(W + args.steps - 1) % N_SETS])
+        want = co.g1_msm(bl, h_sets[last_set])
         dt = time.time() - t
         ok = co.g1_encode(want, False) == res_dev == res_e2e
         cpu_baseline = {"value": n / dt / 1e6, "unit": "Mop/s", "cores": co.num_threads(), "kind": "port",
+                        "threads_busy": "<= %d (bellman's multiexp runs one task per window, c = ceil(ln n))" % (255 // 14 + 1),
                         "sample": "one full 2^%d-term MSM (same bases and scalars as the last timed GPU step), oracle/zk_oracle.c "
                                   "bellman-style Pippenger, %.2f s" % (args.log_n, dt),
                         "matches_gpu_result": bool(ok)}
+        del bl
         if not ok:
             raise SystemExit("PARITY FAILURE: GPU MSM result differs from the oracle")
+    job.close()
+
+    # ---- BASELINE config 5: fixed-total 2^24 MSM sharded over the ranks (strong scaling), closed-form checked ----
+    strong = None
+    if args.strong_log_n and args.secondary:
+        try:
+            strong = strong_scaling_leg(zk, sy, torch, dist, (ctx, ctx2), world, rank, local, args.strong_log_n, steps=3)
+        except SystemExit:
+            raise
+        except Exception as e:
+            strong = {"error": repr(e)}
 
     # batched proving at N > 1 is "replicas only" (SURVEY.md §8e): every rank proves its own 256-proof batch with a resident
     # CRS, no data-path collective; aggregate = all proofs / slowest rank
     replicas = None
     if world > 1 and args.secondary:
         try:
-            g = prove_metrics(ctx, zk, sy, args, batch=256, steps=2, cpu=False)
+            g = prove_metrics(ctx, zk, sy, args, batch=256, steps=2, cpu=False, procs=max(2, (os.cpu_count() or 8) // world))
             t = torch.tensor([g["ms_per_batch"], g["from_witness"]["ms_per_batch"]], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             replicas = {"metric": g["metric"], "scaling": "weak (replicas, no collective)", "batch_per_gpu": 256,
                         "e2e_proofs_per_sec": world * 256 / (float(t[0]) * 1e-3), "from_witness_proofs_per_sec": world * 256 / (float(t[1]) * 1e-3),
-                        "ms_per_batch_max_over_ranks": float(t[0])}
+                        "ms_per_batch_max_over_ranks": float(t[0]), "proofs_checked_per_rank": g["proofs_checked"]}
+        except SystemExit:
+            raise
         except Exception as e:
             replicas = {"error": repr(e)}
     if rank == 0:
@@ -349,33 +523,35 @@ def run_ours(args):
                                    "partial sums all-gathered over NCCL), uniform Fr scalars" % args.log_n,
                        "window_bits": bases.window_bits, "precomputed_window_tables": True,
                        "l2_policy": "inputs larger than L2: %d distinct 32 MiB scalar vectors cycled, %.2f GiB window tables gathered randomly" % (N_SETS, (255 // bases.window_bits + 1) * n * 96 / 2**30),
-                       "setup_s_untimed": round(setup_s, 2)},
+                       "setup_s_untimed": round(setup_s, 2),
+                       "pipelining": "two MSMs in flight on two contexts (futures), tail kernels on a high-priority stream"},
             "e2e": {"value": e2e_value, "unit": "Mop/s", "h2d_bytes_per_step": n * 32 * world, "d2h_bytes_per_step": 96 * world,
                     "ms_per_step": ms_e2e / args.steps,
                     "api": "zk_msm_begin / zk_msm_end (C ABI futures, scalars in pinned host memory, two in flight)" if world == 1 else
                            "H2D copy of the scalars + zk_msm_partial_device_begin + NCCL all-gather + zk_points_fold_begin / zk_msm_end, two in flight"},
             "gpu_launches": (KERNELS_PER_MSM + (1 if world > 1 else 0)) * args.steps * world,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "matches_closed_form": closed_ok,
+            "closed_form": "result == (sum over ranks and terms of s_i * b_i mod r) * G with bases b_i * G; numpy dot products + oracle/pyref.py scalar multiple",
+            "blocking_call": blocking,
         }
-        if blocking is not None:
-            line["config"]["pipelining"] = "two MSMs in flight on two contexts (futures), tail kernels on a high-priority stream"
-            line["blocking_call"] = blocking
+        if fresh is not None:
+            line["blocking_call"]["fresh_bases"] = fresh
+        sec = {}
         if args.secondary and world == 1:
             try:
-                line["secondary"] = secondary_metrics(ctx, zk, sy, args)
+                sec = secondary_metrics(ctx, zk, sy, args)
+            except SystemExit:
+                raise
             except Exception as e:      # the headline line must still print
-                line["secondary"] = {"error": repr(e)}
+                sec = {"error": repr(e)}
         if replicas is not None:
-            line["secondary"] = {"groth16_replicas": replicas}
+            sec["groth16_replicas"] = replicas
+        if strong is not None:
+            sec["msm_strong_scaling"] = strong
+        if sec:
+            line["secondary"] = sec
         print(json.dumps(line), flush=True)
-    # ordered teardown: tensors that were used on the library's stream must be released before the stream is
-    # destroyed with the context (their allocator blocks record events on it when freed)
-    if world > 1:
-        lanes.clear()
-    del d_sets, pinned, d_stage, d_part, d_all
-    torch.cuda.synchronize()
-    torch.cuda.empty_cache()
-    bases.free()
     ctx2.close()
     if world > 1:
         dist.barrier()
@@ -413,10 +589,11 @@ def secondary_metrics(ctx, zk, sy, args):
     return out
 
 
-def prove_metrics(ctx, zk, sy, args, batch=256, steps=3, cpu=True):
-    """proofs/sec for the confidential_transfer-shaped synthetic circuit: batch of 256 witnesses in
-    pinned host memory -> zk_groth16_prove_batch (one C-ABI call per step, H2D of every witness and D2H of the proofs
-    inside the timed region); CPU: the oracle's create_proof on the same CRS and witness, all host threads."""
+def prove_metrics(ctx, zk, sy, args, batch=256, steps=3, cpu=True, procs=None):
+    """proofs/sec for the confidential_transfer-shaped synthetic circuit: a batch of 256 DISTINCT witnesses
+    in pinned host memory -> zk_groth16_prove_batch (one C-ABI call per step, H2D of every witness and D2H of the proofs inside
+    the timed region).  EVERY proof of the batch is compared with the closed-form proof of its witness (trapdoor algebra + big-integer
+    curve arithmetic, computed in host worker processes), the first 8 also with the oracle's create_proof (the CPU baseline)."""
     import torch
     r1cs = sy.make_r1cs(seed=1, **sy.CONF_SHAPE)
     dens = sy.densities(r1cs)
@@ -426,26 +603,43 @@ def prove_metrics(ctx, zk, sy, args, batch=256, steps=3, cpu=True):
     t = time.time()
     params = zk.Parameters.read(ctx, crs.params_bytes, checked=True)
     load_s = time.time() - t
-    n_w = 8                                                          # distinct witnesses, cycled with distinct (r, s)
-    ws = []
-    for k in range(n_w):
-        z = sy.make_witness(r1cs, 100 + k)
-        a, b, c = sy.evaluate(r1cs, z)
-        ws.append([sy.ints_to_limbs(v) for v in (a, b, c, z[:r1cs.n_inputs], z[r1cs.n_inputs:])])
-    def pinned(j):
-        arr = np.stack([ws[k % n_w][j] for k in range(batch)])
-        return torch.from_numpy(arr.view(np.int64)).pin_memory()
-    bufs = [pinned(j) for j in range(5)]
+    t = time.time()
+    wit = make_witnesses(crs, batch, procs or (os.cpu_count() or 8))
+    wit_s = time.time() - t
+    bufs = [torch.from_numpy(np.stack([w[1][j] for w in wit]).view(np.int64)).pin_memory() for j in range(5)]
     views = [t_.numpy().view(np.uint64) for t_ in bufs]
-    rng = sy.SplitMix64(4242)
-    rs = sy.ints_to_limbs([rng.fr() for _ in range(batch)]); ss = sy.ints_to_limbs([rng.fr() for _ in range(batch)])
+    rs = sy.ints_to_limbs([w[2] for w in wit]); ss = sy.ints_to_limbs([w[3] for w in wit])
+    want_all = b"".join(w[4] for w in wit)
     h2d = sum(v.nbytes for v in views) + rs.nbytes + ss.nbytes
     zk.create_proof_batch_raw(params, batch, *views, *dens, rs, ss)          # warm-up (allocations, NTT tables)
     zk.create_proof_batch_raw(params, batch, *views, *dens, rs, ss)
+    ctx.profile(True)                                                        # restarts the device-side work counters
     t = time.perf_counter()
     for _ in range(steps):
         proofs = zk.create_proof_batch_raw(params, batch, *views, *dens, rs, ss)
     dt = (time.perf_counter() - t) / steps
+    g1_adds, g2_adds = ctx.profile_counts()
+    acc_ms, acc_launches = ctx.profile_read()
+    ctx.profile(False)
+    bad = [k for k in range(batch) if proofs[192 * k:192 * (k + 1)] != want_all[192 * k:192 * (k + 1)]]
+    if bad:
+        raise SystemExit("PARITY FAILURE: %d of %d GPU proofs differ from the closed form (first: %d)" % (len(bad), batch, bad[0]))
+    # roofline of the batch: work the kernels EXECUTE, in Fq-product equivalents, against the calibrated integer-multiply peak
+    fq_peak, _ = zk.bench_modmul(ctx, zk.FIELD_FQ, 148 * 4, 256, 3000)
+    fr_peak, _ = zk.bench_modmul(ctx, zk.FIELD_FR, 148 * 4, 256, 3000)
+    log_m = 15
+    ntt_fr = 7 * (1 << (log_m - 1)) * log_m                                   # 7 transforms of 2^15 per proof, (m/2) log m butterflies each
+    per_proof = {"g1_bucket_additions": g1_adds / (steps * batch), "g2_bucket_additions": g2_adds / (steps * batch), "ntt_fr_modmul": ntt_fr}
+    exec_fq = 10.0 * per_proof["g1_bucket_additions"] + 28.0 * per_proof["g2_bucket_additions"] + ntt_fr * fq_peak / fr_peak
+    algo_fq = 176.0 * 80722 + 528.0 * 12402 + ntt_fr * fq_peak / fr_peak          # per-proof algorithmic convention
+    roofline = {"bound": "int32-modmul", "unit": "Fq-modmul/s", "peak": fq_peak,
+                "executed_modmul_per_proof": exec_fq, "executed_frac": exec_fq * batch / dt / fq_peak,
+                "achieved": algo_fq * batch / dt, "frac": algo_fq * batch / dt / fq_peak, "per_proof": per_proof,
+                "g1_accumulate_share_of_batch": acc_ms * 1e-3 / steps / dt,
+                "note": "executed = 10 Fq products per G1 bucket addition + 28 per G2 bucket addition (8 Fq2 products + 2 Fq2 squarings) "
+                        "+ NTT butterflies scaled by the Fr/Fq product cost; additions are counted on the device (non-zero digits), bucket "
+                        "reductions, blinding multiplications and encodings are NOT counted (conservative).  frac uses SURVEY 8(d)'s fixed "
+                        "176 n / 528 n convention, which over-counts the 0/1 witness scalars"}
     # two batches in flight: a second context (own streams and workspace, same resident CRS) driven by a second host thread, so
     # the upload of one batch and the latency-bound tails of its MSMs overlap the other's kernels (ctypes releases the GIL)
     two = None
@@ -494,19 +688,23 @@ def prove_metrics(ctx, zk, sy, args, batch=256, steps=3, cpu=True):
         single = zk.create_proof_batch_raw(params, 1, *[v[:1] for v in views], *dens, rs[:1], ss[:1])
         lat = min(lat, time.perf_counter() - t)
     assert single == proofs[:192]
-    # CPU port of the reference path on the same CRS / witness
+    # CPU port of the reference path on the same CRS / witnesses: the first 8 proofs of the batch, each compared byte for byte
     cpu_block = None
     if cpu:
         from oracle import coracle as co
+        co.set_num_threads(os.cpu_count() or 1)
         op = co.Params(crs.params_bytes, checked=False)
-        r0 = sum(int(x) << (64 * i) for i, x in enumerate(rs[0])); s0 = sum(int(x) << (64 * i) for i, x in enumerate(ss[0]))
-        w0 = [v[0] for v in views]
-        t = time.perf_counter(); want = op.prove(*w0, *dens, r0, s0); cpu_dt = time.perf_counter() - t
-        t = time.perf_counter(); op.prove(*w0, *dens, r0, s0); cpu_dt = min(cpu_dt, time.perf_counter() - t)
-        if want != proofs[:192]:
+        n_cpu = min(8, batch)
+        to_int = lambda row: sum(int(x) << (64 * i) for i, x in enumerate(row))
+        op.prove(*[v[0] for v in views], *dens, to_int(rs[0]), to_int(ss[0]))          # warm-up
+        t = time.perf_counter()
+        cpu_proofs = [op.prove(*[v[k] for v in views], *dens, to_int(rs[k]), to_int(ss[k])) for k in range(n_cpu)]
+        cpu_dt = (time.perf_counter() - t) / n_cpu
+        if b"".join(cpu_proofs) != proofs[:192 * n_cpu]:
             raise SystemExit("PARITY FAILURE: GPU proof bytes differ from the oracle")
         cpu_block = {"value": 1.0 / cpu_dt, "unit": "proofs/s", "cores": co.num_threads(), "kind": "port",
-                     "sample": "oracle create_proof, best of 2, same CRS/witness", "matches_gpu_proof_bytes": True}
+                     "sample": "oracle create_proof on the first %d witnesses of the batch, one after the other, same CRS" % n_cpu,
+                     "matches_gpu_proof_bytes": True}
     params.free()
     try:
         verify_block = verify_metrics(ctx, zk, crs.params_bytes, proofs, np.ascontiguousarray(views[3][:, 1:, :]), cpu)
@@ -519,7 +717,9 @@ def prove_metrics(ctx, zk, sy, args, batch=256, steps=3, cpu=True):
             "d2h_bytes_per_step": 192 * batch, "single_proof_latency_ms": lat * 1e3, "params_load_checked_s": load_s,
             "from_witness": {"e2e_proofs_per_sec": batch / dt_w, "ms_per_batch": dt_w * 1e3, "h2d_bytes_per_step": int(h2d_w),
                              "api": "zk_groth16_prove_witness_batch (constraint system resident, GPU evaluates the R1CS rows)"},
-            "two_batches_in_flight": two, "cpu_baseline": cpu_block, "verify": verify_block,
+            "two_batches_in_flight": two, "cpu_baseline": cpu_block, "verify": verify_block, "roofline": roofline,
+            "proofs_checked": batch, "distinct_witnesses": batch, "witness_generation_s_untimed": wit_s,
+            "check": "every proof of the batch == closed-form proof of its witness (trapdoor algebra + oracle/pyref.py); first 8 == oracle create_proof",
             "timing": "host wall clock around synchronous C-ABI calls (each call ends with a stream synchronise)"}
 
 
@@ -591,36 +791,75 @@ def verify_metrics(ctx, zk, vk_bytes, proofs, inputs, cpu=True, n_v=8192):
 
 
 def run_reference(args):
-    """Reference arm: the CPU restatement of the reference's bellman/pairing path (oracle/zk_oracle.c;
-    the reference itself is Rust and cannot be built here: no cargo/rustc, bellman un-vendored)."""
+    """Reference arm: the reference's own CPU algorithm for the path — the restatement of bellman's multiexp / create_proof in
+    oracle/zk_oracle.c (the reference itself is Rust and cannot be built here: no cargo/rustc, bellman un-vendored) — on ALL host
+    threads of the box, on the SAME config as our arm at this N: one MSM of N * 2^log_n terms per step (weak scaling: the
+    GPUs' shards together are one MSM of that size; the CPU does not get faster with more GPUs)."""
     world, rank = env_int("WORLD_SIZE", 1), env_int("RANK", 0)
     if rank != 0:
         return
     from oracle import coracle as co
     from zero_chain_b200 import synthetic as sy
     co.build()
-    n_full = 1 << args.log_n
-    n = min(n_full, 1 << 18)              # bounded sample of the workload: 2^18 of the 2^20 terms per step
-    bases = co.g1_fixed_base(sy.random_fr_limbs(n, 7))
-    sets = [make_scalars(n, 0, k) for k in range(4)]
-    for k in range(args.warmup):
-        co.g1_msm(bases, sets[k % 4])
+    cores = os.cpu_count() or 1
+    co.set_num_threads(cores)              # torchrun exports OMP_NUM_THREADS=1: the baseline is "all host threads", set explicitly
+    n = (1 << args.log_n) * max(1, args.gpus)
+    bs = sy.random_fr_limbs(n, 7)
+    bs[:, 1:] = 0                          # bases b_i * G with 64-bit b_i: 4x cheaper to generate on the CPU; the cost of an MSM does not depend on them
     t0 = time.time()
-    for k in range(args.steps):
-        co.g1_msm(bases, sets[(args.warmup + k) % 4])
+    bases = co.g1_fixed_base(bs)
+    setup_s = time.time() - t0
+    sets = [sy.random_fr_limbs(n, 1000 + k) for k in range(2)]
+    t0 = time.time()
+    co.g1_msm(bases, sets[0])              # first warm-up step, also sizes the run
+    t1 = time.time() - t0
+    warmup = max(1, min(args.warmup, int(30.0 / t1)))
+    steps = max(1, min(args.steps, int(100.0 / t1)))
+    for k in range(1, warmup):
+        co.g1_msm(bases, sets[k % 2])
+    t0 = time.time()
+    for k in range(steps):
+        co.g1_msm(bases, sets[(warmup + k) % 2])
     dt = time.time() - t0
-    value = n * args.steps / dt / 1e6
-    cores = co.num_threads()
+    value = n * steps / dt / 1e6
+    c_win = max(3, int(np.ceil(np.log(n))))
+    busy = 255 // c_win + 1
+    sample = "full config: %d-term MSM per step (N * 2^%d), %d timed steps after %d warm-up (requested %d / %d, bounded to ~2 minutes)" % (
+        n, args.log_n, steps, warmup, args.steps, args.warmup)
     line = {"impl": "reference", "metric": "g1_msm_mops_2^%d" % args.log_n, "value": value, "unit": "Mop/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
+            "steps": steps, "warmup": warmup, "steps_requested": args.steps, "ms_per_step": dt * 1e3 / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64-limb Montgomery, integer", "data": "synthetic",
-            "config": {"workload": "G1 Pippenger MSM (bellman multiexp restatement, c = ceil(ln n), one thread per window), "
-                                   "bounded sample: 2^18 of the 2^%d terms per step" % args.log_n},
-            "cpu_baseline": {"value": value, "unit": "Mop/s", "cores": cores, "kind": "port",
-                             "sample": "2^18-term MSM per step, %d steps, all %d host threads" % (args.steps, cores)},
+            "config": {"workload": "G1 Pippenger MSM, 2^%d bases per GPU x %d = %d terms in one MSM on the host CPU (bellman multiexp restatement, "
+                                   "c = ceil(ln n) = %d, one task per window)" % (args.log_n, max(1, args.gpus), n, c_win),
+                       "threads": cores, "threads_busy": "<= %d (one task per window, as bellman's multiexp schedules it)" % busy,
+                       "setup_s_untimed": round(setup_s, 2)},
+            "cpu_baseline": {"value": value, "unit": "Mop/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "Mop/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if args.secondary:
+        try:
+            line["secondary"] = {"groth16": reference_prove_metrics(co, sy, cores)}
+        except Exception as e:
+            line["secondary"] = {"error": repr(e)}
     print(json.dumps(line), flush=True)
+
+
+def reference_prove_metrics(co, sy, cores):
+    """proofs/sec of the CPU restatement of create_proof on the confidential_transfer-shaped synthetic circuit (same R1CS, toy CRS
+    seeds and witness seeds as our arm's secondary.groth16), all host threads, one proof after the other (zface proves one at a time)."""
+    r1cs = sy.make_r1cs(seed=1, **sy.CONF_SHAPE)
+    dens = sy.densities(r1cs)
+    crs = sy.make_toy_crs(r1cs, co.g1_fixed_base, co.g2_fixed_base, seed=2)
+    op = co.Params(crs.params_bytes, checked=False)
+    _wk_init(crs)
+    wit = [_wk_witness(k) for k in range(4)]
+    op.prove(*wit[0][1], *dens, wit[0][2], wit[0][3])
+    t = time.perf_counter()
+    out = [op.prove(*w[1], *dens, w[2], w[3]) for w in wit]
+    dt = (time.perf_counter() - t) / len(wit)
+    ok = all(o == w[4] for o, w in zip(out, wit))
+    return {"metric": "proofs_per_sec (confidential_transfer shape: 19974 constraints, 23 inputs, domain 2^15; synthetic R1CS, toy CRS)",
+            "e2e_proofs_per_sec": 1.0 / dt, "ms_per_proof": dt * 1e3, "cores": cores, "proofs": len(wit), "matches_closed_form": bool(ok)}
 
 
 def main():
@@ -633,6 +872,8 @@ def main():
     ap.add_argument("--window-bits", dest="window_bits", type=int, default=0, help="0 = library default (20 bits from 2^20 terms, else <= 16)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-secondary", dest="secondary", action="store_false")
+    ap.add_argument("--strong-log-n", dest="strong_log_n", type=int, default=24,
+                    help="total terms (log2) of the fixed-total sharded MSM of secondary.msm_strong_scaling (BASELINE config 5); 0 = skip")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     if args.impl == "reference":

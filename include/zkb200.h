@@ -190,6 +190,10 @@ int zk_bench_modmul(zk_ctx *ctx, int field, int blocks, int threads, int iters, 
  * count (bench.py's roofline block).  Disabled by default (no events are created). */
 int zk_ctx_profile(zk_ctx *ctx, int enable);
 int zk_ctx_profile_read(zk_ctx *ctx, double *total_ms, uint64_t *launches);
+/* Work executed by the MSMs of this context (and of its prover lanes) since the last zk_ctx_profile call: the number of bucket
+ * additions (= non-zero signed digits) in G1 and in G2, counted on the device.  bench.py turns them into executed
+ * Fq-modmul-equivalents for the proofs/sec roofline (one mixed addition = 10 products in the base field). */
+int zk_ctx_profile_counts(zk_ctx *ctx, uint64_t *g1_additions, uint64_t *g2_additions);
 
 /* ---- Groth16 verification (the step after the proving path) ----------------------------------
  * zk_pvk: bellman_verifier::PreparedVerifyingKey<Bls12> resident on the device — e(alpha_g1, beta_g2), the Miller-loop

@@ -157,7 +157,8 @@ def test_msm_batch_matches_single(ctx):
     b.free()
 
 
-def test_msm_2_20_closed_form_full_size(ctx):
+@pytest.mark.parametrize("window_bits", [16, 0])      # 0 = the library default at this size (20-bit windows, what bench.py runs)
+def test_msm_2_20_closed_form_full_size(ctx, window_bits):
     """BASELINE config size (2^20 terms), checked without the oracle's O(n) curve work: bases P_i = (i+1)*G
     (the construction of the reference's vector files) give  sum s_i P_i = (sum s_i (i+1) mod r) * G."""
     n = 1 << 20
@@ -166,7 +167,8 @@ def test_msm_2_20_closed_form_full_size(ctx):
     assert np.array_equal(bases[:3], co.g1_fixed_base(idx[:3])) and np.array_equal(bases[-1], co.g1_fixed_base(idx[-1:])[0])
     scal = sy.random_fr_limbs(n, 2020)
     scal[:4] = co.ints_to_limbs([0, 1, pr.R - 1, 2], 4)
-    b = zk.Bases(ctx, 1, bases, window_bits=16, precompute=True)
+    b = zk.Bases(ctx, 1, bases, window_bits=window_bits, precompute=True)
+    assert b.window_bits == (window_bits or 20)
     got = zk.multiexp(b, scal)
     s = scal.astype(object)
     vals = s[:, 0] + (s[:, 1] << 64) + (s[:, 2] << 128) + (s[:, 3] << 192)

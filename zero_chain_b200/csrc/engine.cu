@@ -380,6 +380,22 @@ extern "C" int zk_ctx_profile(zk_ctx *ctx, int enable) {
     for (cudaEvent_t ev : ctx->prof_events) cudaEventDestroy(ev);
     ctx->prof_events.clear();
     ctx->prof_on = enable != 0;
+    for (zk_ctx *c : {ctx, ctx->aux, ctx->aux2})             // work counters of this context and its lanes restart with the profile
+        if (c) { ZK_CUDA(cudaStreamSynchronize(c->stream)); ZK_CUDA(cudaMemsetAsync(c->d_err + 10, 0, 4 * sizeof(int), c->stream)); ZK_CUDA(cudaStreamSynchronize(c->stream)); }
+    return ZK_OK;
+}
+extern "C" int zk_ctx_profile_counts(zk_ctx *ctx, uint64_t *g1_additions, uint64_t *g2_additions) {
+    if (!ctx || !g1_additions || !g2_additions) { zk_set_error("zk_ctx_profile_counts: NULL argument"); return ZK_ERR_INVALID; }
+    ZK_TRY(zk_use_device(ctx));
+    *g1_additions = 0; *g2_additions = 0;
+    for (zk_ctx *c : {ctx, ctx->aux, ctx->aux2}) {
+        if (!c) continue;
+        unsigned long long v[2] = {0, 0};
+        ZK_CUDA(cudaStreamSynchronize(c->stream));
+        if (c->tail) ZK_CUDA(cudaStreamSynchronize(c->tail));
+        ZK_CUDA(cudaMemcpy(v, c->d_err + 10, sizeof(v), cudaMemcpyDeviceToHost));
+        *g1_additions += v[0]; *g2_additions += v[1];
+    }
     return ZK_OK;
 }
 extern "C" int zk_ctx_profile_read(zk_ctx *ctx, double *total_ms, uint64_t *launches) {

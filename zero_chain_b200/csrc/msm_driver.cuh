@@ -118,7 +118,8 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
     }
     uint32_t *d_task_len = (uint32_t *)(ctx->d_err + 8);
     const uint32_t capacity = (uint32_t)ctx->sm_count * 3u * 128u;      // k_accumulate: 3 CTAs of 128 threads per SM
-    k_pick_task_len<<<1, 1, 0, st>>>(cur_off + NB, d_task_len, capacity);
+    unsigned long long *d_work = (unsigned long long *)(ctx->d_err + (sizeof(F) == sizeof(Fq) ? 10 : 12));   // G1 / G2 addition counters
+    k_pick_task_len<<<1, 1, 0, st>>>(cur_off + NB, d_task_len, capacity, d_work);
     exclusive_scan<true>(cur_sizes, ctx->task_off.as<uint32_t>(), NB, ctx->scan_scratch.as<uint32_t>(), st, d_task_len);
     // 3. accumulate + combine.  The payload of an entry is its position in the domain = [w][i] index;
     //    with tables that is the table index when n == b->n (checked by the callers).

@@ -77,6 +77,12 @@ class Context:
         _ck(_lib.lib().zk_ctx_profile_read(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def profile_counts(self):
+        """(G1 bucket additions, G2 bucket additions) executed by this context's MSMs (lanes included) since profile()."""
+        a, b = C.c_uint64(), C.c_uint64()
+        _ck(_lib.lib().zk_ctx_profile_counts(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def close(self):
         if self._h:
             _lib.lib().zk_ctx_destroy(self._h)
