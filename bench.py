@@ -41,6 +41,14 @@ ALGO_MODMUL_PER_TERM = 176     # 11 (mixed add) x ceil(255/16) windows — the F
 ALGO_BYTES_PER_TERM = 128      # 96 B base + 32 B scalar
 
 
+def host_cores():
+    """CPUs this process may run on (the box's cgroup / affinity mask, not the machine's logical CPU count)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def env_int(name, default):
     try:
         return int(os.environ.get(name, default))
@@ -473,7 +481,7 @@ def run_ours(args):
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import coracle as co
-        co.set_num_threads(os.cpu_count() or 1)
+        co.set_num_threads(host_cores())
         bl = co.g1_fixed_base(base_scalars)           # the same bases, made by the oracle's own fixed-base code
         t = time.time()
         want = co.g1_msm(bl, h_sets[last_set])
@@ -504,7 +512,7 @@ def run_ours(args):
     replicas = None
     if world > 1 and args.secondary:
         try:
-            g = prove_metrics(ctx, zk, sy, args, batch=256, steps=2, cpu=False, procs=max(2, (os.cpu_count() or 8) // world))
+            g = prove_metrics(ctx, zk, sy, args, batch=256, steps=2, cpu=False, procs=max(2, min(24, host_cores() // world)))
             t = torch.tensor([g["ms_per_batch"], g["from_witness"]["ms_per_batch"]], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             replicas = {"metric": g["metric"], "scaling": "weak (replicas, no collective)", "batch_per_gpu": 256,
@@ -604,7 +612,7 @@ def prove_metrics(ctx, zk, sy, args, batch=256, steps=3, cpu=True, procs=None):
     params = zk.Parameters.read(ctx, crs.params_bytes, checked=True)
     load_s = time.time() - t
     t = time.time()
-    wit = make_witnesses(crs, batch, procs or (os.cpu_count() or 8))
+    wit = make_witnesses(crs, batch, procs or min(24, host_cores()))
     wit_s = time.time() - t
     bufs = [torch.from_numpy(np.stack([w[1][j] for w in wit]).view(np.int64)).pin_memory() for j in range(5)]
     views = [t_.numpy().view(np.uint64) for t_ in bufs]
@@ -692,7 +700,7 @@ def prove_metrics(ctx, zk, sy, args, batch=256, steps=3, cpu=True, procs=None):
     cpu_block = None
     if cpu:
         from oracle import coracle as co
-        co.set_num_threads(os.cpu_count() or 1)
+        co.set_num_threads(host_cores())
         op = co.Params(crs.params_bytes, checked=False)
         n_cpu = min(8, batch)
         to_int = lambda row: sum(int(x) << (64 * i) for i, x in enumerate(row))
@@ -801,7 +809,7 @@ def run_reference(args):
     from oracle import coracle as co
     from zero_chain_b200 import synthetic as sy
     co.build()
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     co.set_num_threads(cores)              # torchrun exports OMP_NUM_THREADS=1: the baseline is "all host threads", set explicitly
     n = (1 << args.log_n) * max(1, args.gpus)
     bs = sy.random_fr_limbs(n, 7)

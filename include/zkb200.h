@@ -55,6 +55,15 @@ typedef struct zk_ctx zk_ctx;
 int zk_ctx_create(int device, void *stream, zk_ctx **out);
 void zk_ctx_destroy(zk_ctx *ctx);
 int zk_ctx_sync(zk_ctx *ctx);
+/* Tuning options of a context (and of the prover lanes it owns).  Results never depend on them.
+ *   ZK_OPT_AFFINE_MIN_ENTRIES  MSMs with at least this many (term, window) entries reduce their buckets with batched-affine
+ *                              rounds (6 field products per addition instead of 10, one shared inversion per round, ~0.15 ms of
+ *                              latency each) before the XYZZ pass.  Default -1 = never: on B200 the rounds measured no faster
+ *                              than the XYZZ pass alone (profiles/r02_experiments.md); 0 = always.
+ *   ZK_OPT_AFFINE_LEVELS       number of rounds; -1 (default) = from the average bucket length. */
+#define ZK_OPT_AFFINE_MIN_ENTRIES 1
+#define ZK_OPT_AFFINE_LEVELS 2
+int zk_ctx_set_opt(zk_ctx *ctx, int opt, long value);
 void *zk_ctx_stream(zk_ctx *ctx);
 
 /* ---- multi-scalar multiplication (replaces bellman::multiexp::multiexp) ----- */

@@ -61,7 +61,7 @@ void emu_g1_mul(const uint32_t *a, const uint32_t *k, uint32_t *o) { t_mul<Fq>(a
 void emu_g2_mul(const uint32_t *a, const uint32_t *k, uint32_t *o) { t_mul<Fq2>(a, k, o); }
 }
 
-// ---- batched-affine pair additions (msm_affine.cuh): the per-pair classification / finish functions and the
+// ---- batched-affine pair additions (msm_batchaff.cuh, msm_affine_core.cuh): the per-pair classification / finish functions and the
 // simultaneous-inversion walk, replayed on the host for ONE bucket of n points -> ceil(n/2) points
 #include <vector>
 #include "msm_affine_core.cuh"

@@ -20,6 +20,7 @@ SIGNATURES = {
     "zk_ctx_create": (i32, [i32, vp, PP]),
     "zk_ctx_destroy": (None, [vp]),
     "zk_ctx_sync": (i32, [vp]),
+    "zk_ctx_set_opt": (i32, [vp, i32, C.c_long]),
     "zk_ctx_stream": (vp, [vp]),
     "zk_bases_upload": (i32, [vp, i32, vp, sz, i32, i32, PP]),
     "zk_bases_free": (None, [vp]),

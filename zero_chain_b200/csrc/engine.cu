@@ -51,7 +51,7 @@ extern "C" void zk_ctx_destroy(zk_ctx *c) {
     DevBuf *bufs[] = {&c->scalars, &c->digits, &c->tile_hist, &c->tile_off, &c->sizes, &c->bucket_off, &c->task_off, &c->scan_scratch,
                       &c->sorted, &c->partials, &c->buckets, &c->red_part, &c->red_x, &c->result, &c->out_bytes, &c->stage_a, &c->stage_b,
                       &c->stage_c, &c->ntt_tmp, &c->g_a, &c->g_b, &c->g_c, &c->g_h, &c->g_scal, &c->g_misc,
-                      &c->aff_pts0, &c->aff_pts1, &c->aff_scratch, &c->aff_off0, &c->aff_off1, &c->aff_sizes0, &c->aff_sizes1, &c->red_rows, &c->g_scal2, &c->g_scal3, &c->sorted2, &c->coarse_off, &c->coarse_sizes, &c->task_order, &c->len_hist, &c->heavy_list, &c->red_tmp,
+                      &c->aff_pts0, &c->aff_pts1, &c->aff_scratch, &c->aff_off0, &c->aff_off1, &c->aff_sizes0, &c->aff_sizes1, &c->aff_srcs, &c->aff_tot, &c->red_rows, &c->g_scal2, &c->g_scal3, &c->sorted2, &c->coarse_off, &c->coarse_sizes, &c->task_order, &c->len_hist, &c->heavy_list, &c->red_tmp,
                       &c->v_pts, &c->v_stat, &c->v_coef, &c->v_f, &c->v_part, &c->v_io};
     for (DevBuf *b : bufs) b->release();
     for (NttSlot &sl : c->ntt_slots) { sl.w.release(); sl.g.release(); sl.gi.release(); sl.consts.release(); }
@@ -60,6 +60,16 @@ extern "C" void zk_ctx_destroy(zk_ctx *c) {
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
+}
+extern "C" int zk_ctx_set_opt(zk_ctx *c, int opt, long value) {
+    if (!c) { zk_set_error("zk_ctx_set_opt: NULL ctx"); return ZK_ERR_INVALID; }
+    for (zk_ctx *x : {c, c->aux, c->aux2}) {
+        if (!x) continue;
+        if (opt == ZK_OPT_AFFINE_MIN_ENTRIES) x->opts.ba_min_entries = value;
+        else if (opt == ZK_OPT_AFFINE_LEVELS) x->opts.ba_levels = value;
+        else { zk_set_error("zk_ctx_set_opt: unknown option %d", opt); return ZK_ERR_INVALID; }
+    }
+    return ZK_OK;
 }
 extern "C" int zk_ctx_sync(zk_ctx *c) { ZK_TRY(zk_use_device(c)); return zk_check_err_flag(c); }   // synchronises; reports a pending device-side error flag
 extern "C" void *zk_ctx_stream(zk_ctx *c) { return (void *)c->stream; }
@@ -354,6 +364,9 @@ extern "C" int zk_field_op(zk_ctx *ctx, int field, int op, const uint64_t *a, co
 
 extern "C" int zk_bench_modmul(zk_ctx *ctx, int field, int blocks, int threads, int iters, double *per_s, double *ms_out) {
     if (!ctx || !per_s) { zk_set_error("zk_bench_modmul: NULL argument"); return ZK_ERR_INVALID; }
+#ifndef ZK_EXPERIMENTS
+    if (field != 0 && field != 1) { zk_set_error("zk_bench_modmul: field must be 0 (Fq) or 1 (Fr)"); return ZK_ERR_INVALID; }
+#endif
     ZK_TRY(zk_use_device(ctx));
     ZK_TRY(ctx->stage_a.reserve(64));
     cudaEvent_t e0, e1;

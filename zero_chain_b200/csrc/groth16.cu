@@ -436,10 +436,10 @@ static int prove_impl(zk_ctx *ctx, const zk_params *p, size_t batch,
     size_t max_scal = nH; if (nA > max_scal) max_scal = nA; if (nB > max_scal) max_scal = nB;
     ZK_TRY(ctx->g_scal.reserve(batch * max_scal * 32));
     ZK_TRY(ctx->g_scal2.reserve(batch * nB * 32));
-    if (!ctx->aux) ZK_TRY(zk_ctx_create(ctx->device, nullptr, &ctx->aux));      // second lane for the G2 MSM
+    if (!ctx->aux) { ZK_TRY(zk_ctx_create(ctx->device, nullptr, &ctx->aux)); ctx->aux->opts = ctx->opts; }      // second lane for the G2 MSM
     zk_ctx *lane2 = ctx->aux;
     ZK_TRY(ctx->g_scal3.reserve(batch * nA * 32));
-    if (!ctx->aux2) ZK_TRY(zk_ctx_create(ctx->device, nullptr, &ctx->aux2));    // third lane for the A and B1 MSMs
+    if (!ctx->aux2) { ZK_TRY(zk_ctx_create(ctx->device, nullptr, &ctx->aux2)); ctx->aux2->opts = ctx->opts; }    // third lane for the A and B1 MSMs
     zk_ctx *lane3 = ctx->aux2;
     auto rnd = [](size_t b) { return (b + 255) & ~(size_t)255; };
     size_t misc_bytes = rnd(a_idx.size() * 4 + 4) + rnd(bi_idx.size() * 4 + 4) + rnd(ba_idx.size() * 4 + 4) + 2 * rnd(batch * 32) + rnd(batch * 128) +

@@ -41,14 +41,21 @@ struct DevBuf {
 // one cached set of NTT twiddle tables (ntt.cu)
 struct NttSlot { unsigned log_n = 0; bool valid = false; uint64_t last_use = 0; DevBuf w, g, gi, consts; };
 
+// tuning options of a context (zk_ctx_set_opt); the prover lanes inherit them
+struct zk_opts {
+    long ba_min_entries = -1;          // ZK_OPT_AFFINE_MIN_ENTRIES; -1 = batched-affine rounds off (the measured default, profiles/r02_experiments.md)
+    long ba_levels = -1;               // ZK_OPT_AFFINE_LEVELS (-1 = from the average bucket length)
+};
+
 struct zk_ctx {
+    zk_opts opts;
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int sm_count = 0;
     int *d_err = nullptr;          // device error flag (non-canonical scalar etc.)
     // MSM workspace
-    DevBuf aff_pts0, aff_pts1, aff_scratch, aff_off0, aff_off1, aff_sizes0, aff_sizes1;   // batched-affine levels
+    DevBuf aff_pts0, aff_pts1, aff_scratch, aff_off0, aff_off1, aff_sizes0, aff_sizes1, aff_srcs, aff_tot;   // batched-affine rounds (msm_batchaff.cuh)
     DevBuf scalars, digits, tile_hist, tile_off, sizes, bucket_off, task_off, scan_scratch, sorted, partials, buckets, red_part, red_x, red_rows, sorted2, coarse_off, coarse_sizes, task_order, len_hist, heavy_list, red_tmp, result, out_bytes;
     bool len_hist_zeroed = false;
     // generic staging

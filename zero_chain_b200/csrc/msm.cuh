@@ -193,11 +193,11 @@ __device__ __forceinline__ uint32_t scan_load(const uint32_t *in, size_t i, uint
 // Task length from the number of non-zero entries (bucket_off[NB]).  Tasks all take the same time, so the
 // accumulation kernel runs in waves of `capacity` (= resident threads) tasks; the length is chosen so that the
 // task count is just under a whole number of waves (a trailing partial wave costs a full wave's latency).
-static __global__ void k_pick_task_len(const uint32_t *__restrict__ total_entries, uint32_t *__restrict__ task_len, uint32_t capacity,
-                                       unsigned long long *__restrict__ work_counter) {
+static __global__ void k_pick_task_len(const uint32_t *__restrict__ total_entries, const uint32_t *__restrict__ sorted_entries, uint32_t *__restrict__ task_len,
+                                       uint32_t capacity, unsigned long long *__restrict__ work_counter) {
     task_len[1] = 0;                                           // heavy-bucket counter of k_combine_serial (next word)
-    uint32_t total = *total_entries;
-    *work_counter += total;                                    // executed bucket additions (non-zero digits) of this context, read by zk_ctx_profile_counts
+    uint32_t total = *total_entries;                           // entries the XYZZ pass sees (after the batched-affine rounds)
+    *work_counter += *sorted_entries;                                    // executed bucket additions (non-zero digits) of this context, read by zk_ctx_profile_counts
     uint32_t waves = (total + (uint32_t)TASK_LEN_MAX * capacity - 1) / ((uint32_t)TASK_LEN_MAX * capacity);
     if (waves < 2) waves = 2;                                   // small inputs: at least two waves of short tasks
     uint32_t target = (uint32_t)(0.97f * (float)waves * (float)capacity);

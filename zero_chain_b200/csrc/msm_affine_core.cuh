@@ -1,4 +1,4 @@
-// Per-pair pieces of the batched-affine bucket pre-reduction (see msm_affine.cuh): classification of a pair,
+// Per-pair pieces of the batched-affine bucket reduction (see msm_batchaff.cuh): classification of a pair,
 // its denominator, and the affine addition / doubling given the inverted denominator.  Plain device functions
 // with no CUDA-runtime dependency so the host emulation (tests/host_emul) compiles the same source.
 #pragma once
@@ -30,7 +30,12 @@ ZK_DEV int pair_classify(const Affine<F> &p0, const Affine<F> &p1, bool has1, F 
     if (!has1 || p1.is_inf()) return PAIR_COPY0;
     if (p0.is_inf()) return PAIR_COPY1;
     if (p0.x == p1.x) {
-        if (p0.y == p1.y) { den = p0.y.dbl(); return PAIR_DBL; }      // y != 0: the curves have no 2-torsion
+        if (p0.y == p1.y) {
+            den = p0.y.dbl();
+            if (!den.is_zero()) return PAIR_DBL;
+            den = F::one();                                             // y = 0: a 2-torsion point (only an unchecked, malformed base can be one): 2P = O,
+            return PAIR_INF;                                            // and the shared product of denominators must stay non-zero
+        }
         return PAIR_INF;                                                // P + (-P)
     }
     den = p1.x - p0.x;

@@ -3,7 +3,7 @@
 #pragma once
 #include "internal.h"
 #include "msm.cuh"
-#include "msm_affine.cuh"
+#include "msm_batchaff.cuh"
 #include "codec.cuh"
 #include <stdlib.h>
 
@@ -85,41 +85,84 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
         k_fine_sort<<<dim3(512, (unsigned)n_dom), 1024, 0, st>>>(ctx->sorted2.as<uint32_t>(), ctx->coarse_off.as<uint32_t>(), digits, e_dom, 512, low,
                                                                  ctx->sizes.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(), ctx->sorted.as<uint32_t>());
     }
-    // 2b. batched-affine pre-reduction (msm_affine.cuh): each level halves every bucket at ~6.4 products per addition
-    //     instead of the 10 of an XYZZ mixed addition.  MEASURED (round 1, 2^20 terms): 9.1 ms (1 level) / 9.3 ms (2 levels)
-    //     against 8.3 ms without — the per-thread binary-Euclid inversion diverges inside a warp and the two passes over
-    //     the gathered points are latency-bound — so it is OFF unless ZK_AFF_LEVELS=1|2 is set (kept: it is correct,
-    //     parity-tested, and the starting point for a block-level shared inversion).
+    // 2b. batched-affine rounds (msm_batchaff.cuh): each round halves every bucket at ~6.3 products per addition instead of the 10
+    //     of an XYZZ mixed addition, with ONE shared field inversion per round.  The number of rounds follows the average bucket
+    //     length (the host only knows the upper bound E / NB; sparse scalars make the rounds cheaper, not wrong): the XYZZ pass
+    //     that follows wants ~3 points per bucket left.
     const Affine<F> *cur_pts = (const Affine<F> *)b->d_tbl;
     const uint32_t *cur_sorted = ctx->sorted.as<uint32_t>(), *cur_off = ctx->bucket_off.as<uint32_t>(), *cur_sizes = ctx->sizes.as<uint32_t>();
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (ctx->prof_on) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, st); }
     {
-        static int lv_env = -2;
-        if (lv_env == -2) { const char *e = getenv("ZK_AFF_LEVELS"); lv_env = e ? atoi(e) : -1; }
-        size_t avg = E / NB;
-        int levels = lv_env >= 0 ? lv_env : 0;
-        (void)avg;
-        if (levels > 2) levels = 2;
+        int levels = 0;
+        if (ctx->opts.ba_min_entries >= 0 && (long)E >= ctx->opts.ba_min_entries) {      // a round costs ~0.1 ms of latency (its inversion): small MSMs stay on the XYZZ pass alone
+            if (ctx->opts.ba_levels >= 0) levels = (int)(ctx->opts.ba_levels < BA_MAX_LEVELS ? ctx->opts.ba_levels : BA_MAX_LEVELS);
+            else for (size_t avg = E / NB; avg >= 6 && levels < BA_MAX_LEVELS; avg >>= 1) levels++;
+        }
         size_t in_max = E;
+        int minb = BA_MINB, k_force = 0;
+#ifdef ZK_EXPERIMENTS
+        if (const char *e = getenv("ZK_BA_MINB")) minb = atoi(e);
+        if (const char *e = getenv("ZK_BA_K")) k_force = atoi(e);
+#endif
         DevBuf *pts_buf[2] = {&ctx->aff_pts0, &ctx->aff_pts1}, *off_buf[2] = {&ctx->aff_off0, &ctx->aff_off1}, *sz_buf[2] = {&ctx->aff_sizes0, &ctx->aff_sizes1};
+        if (levels > 0) {
+            if (ba_smem_backward<F>() > 48 * 1024) {
+                ZK_CUDA(cudaFuncSetAttribute(k_ba_backward<F, true, BA_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba_smem_backward<F>()));
+                ZK_CUDA(cudaFuncSetAttribute(k_ba_backward<F, false, BA_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba_smem_backward<F>()));
+#ifdef ZK_EXPERIMENTS
+                ZK_CUDA(cudaFuncSetAttribute(k_ba_backward<F, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba_smem_backward<F>()));
+                ZK_CUDA(cudaFuncSetAttribute(k_ba_backward<F, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba_smem_backward<F>()));
+#endif
+            }
+            if (ba_smem_invert<F>() > 48 * 1024)
+                ZK_CUDA(cudaFuncSetAttribute(k_ba_invert<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba_smem_invert<F>()));
+        }
         for (int l = 0; l < levels; l++) {
-            size_t out_max = (in_max + NB) / 2 + 1;
-            ZK_TRY(pts_buf[l]->reserve(out_max * sizeof(Affine<F>)));
-            ZK_TRY(off_buf[l]->reserve((NB + 1) * 4)); ZK_TRY(sz_buf[l]->reserve((NB + 1) * 4));
-            ZK_TRY(ctx->aff_scratch.reserve(out_max * sizeof(F)));
-            k_half_sizes<<<(unsigned)((NB + 255) / 256), 256, 0, st>>>(cur_off, sz_buf[l]->as<uint32_t>(), (uint32_t)NB);
-            exclusive_scan<false>(sz_buf[l]->as<uint32_t>(), off_buf[l]->as<uint32_t>(), NB, ctx->scan_scratch.as<uint32_t>(), st);
-            size_t n_thr = (out_max + AFF_B - 1) / AFF_B;
-            k_affine_round<F><<<(unsigned)((n_thr + 127) / 128), 128, 0, st>>>(cur_pts, cur_sorted, cur_off, off_buf[l]->as<uint32_t>(), (uint32_t)NB,
-                                                                              ctx->aff_scratch.as<F>(), pts_buf[l]->as<Affine<F>>());
-            cur_pts = pts_buf[l]->as<Affine<F>>(); cur_sorted = nullptr;
-            cur_off = off_buf[l]->as<uint32_t>(); cur_sizes = sz_buf[l]->as<uint32_t>();
+            const size_t out_max = (in_max + NB) / 2 + 1;
+            // additions per thread: as many as leave >= ~4 waves of blocks (the block-level product trees cost a fixed ~24 warp-products)
+            int K = (int)(out_max / ((size_t)BA_T * ctx->sm_count * BA_MINB * 4));
+            K = K < BA_K_MIN ? BA_K_MIN : (K > BA_K_MAX ? BA_K_MAX : K);
+            if (k_force > 0) K = k_force;
+            const unsigned grid = (unsigned)((out_max + (size_t)BA_T * K - 1) / ((size_t)BA_T * K));
+            const size_t T_total = (size_t)grid * BA_T;
+            DevBuf *pts_o = pts_buf[l & 1], *off_o = off_buf[l & 1], *sz_o = sz_buf[l & 1];
+            ZK_TRY(pts_o->reserve(out_max * sizeof(Affine<F>)));
+            ZK_TRY(off_o->reserve((NB + 1) * 4)); ZK_TRY(sz_o->reserve((NB + 1) * 4));
+            ZK_TRY(ctx->aff_scratch.reserve((size_t)(K + 1) * T_total * sizeof(F)));
+            ZK_TRY(ctx->aff_srcs.reserve(out_max * sizeof(uint2)));
+            ZK_TRY(ctx->aff_tot.reserve(3 * (size_t)grid * sizeof(F)));
+            F *tot = ctx->aff_tot.as<F>(), *tot_scr = tot + grid, *tot_inv = tot + 2 * (size_t)grid;
+            k_half_sizes<<<(unsigned)((NB + 255) / 256), 256, 0, st>>>(cur_off, sz_o->as<uint32_t>(), (uint32_t)NB);
+            exclusive_scan<false>(sz_o->as<uint32_t>(), off_o->as<uint32_t>(), NB, ctx->scan_scratch.as<uint32_t>(), st);
+            const uint32_t *off_out = off_o->as<uint32_t>();
+            if (l == 0)
+                k_ba_forward<F, true><<<grid, BA_T, ba_smem_forward<F>(), st>>>(cur_pts, cur_sorted, cur_off, off_out, (uint32_t)NB, K, ctx->aff_scratch.as<F>(),
+                                                                               ctx->aff_srcs.as<uint2>(), tot);
+            else
+                k_ba_forward<F, false><<<grid, BA_T, ba_smem_forward<F>(), st>>>(cur_pts, nullptr, cur_off, off_out, (uint32_t)NB, K, ctx->aff_scratch.as<F>(),
+                                                                                ctx->aff_srcs.as<uint2>(), tot);
+            k_ba_invert<F><<<1, BA_INV_T, ba_smem_invert<F>(), st>>>(tot, off_out, (uint32_t)NB, K, tot_scr, tot_inv);
+            int Kb = K;
+#ifdef ZK_EXPERIMENTS
+            if (getenv("ZK_BA_NOTREE")) Kb = -K;
+#endif
+#define ZK_BA_BWD(FIRST_, MB_) k_ba_backward<F, FIRST_, MB_><<<grid, BA_T, ba_smem_backward<F>(), st>>>(cur_pts, off_out, (uint32_t)NB, Kb, ctx->aff_scratch.as<F>(), \
+                                                                                                    ctx->aff_srcs.as<uint2>(), tot_inv, pts_o->as<Affine<F>>())
+#ifdef ZK_EXPERIMENTS
+            if (minb == 4) { if (l == 0) ZK_BA_BWD(true, 4); else ZK_BA_BWD(false, 4); } else
+#endif
+            { if (l == 0) ZK_BA_BWD(true, BA_MINB); else ZK_BA_BWD(false, BA_MINB); }
+#undef ZK_BA_BWD
+            cur_pts = pts_o->as<Affine<F>>(); cur_sorted = nullptr;
+            cur_off = off_out; cur_sizes = sz_o->as<uint32_t>();
             in_max = out_max;
         }
     }
     uint32_t *d_task_len = (uint32_t *)(ctx->d_err + 8);
     const uint32_t capacity = (uint32_t)ctx->sm_count * 3u * 128u;      // k_accumulate: 3 CTAs of 128 threads per SM
     unsigned long long *d_work = (unsigned long long *)(ctx->d_err + (sizeof(F) == sizeof(Fq) ? 10 : 12));   // G1 / G2 addition counters
-    k_pick_task_len<<<1, 1, 0, st>>>(cur_off + NB, d_task_len, capacity, d_work);
+    k_pick_task_len<<<1, 1, 0, st>>>(cur_off + NB, ctx->bucket_off.as<uint32_t>() + NB, d_task_len, capacity, d_work);
     exclusive_scan<true>(cur_sizes, ctx->task_off.as<uint32_t>(), NB, ctx->scan_scratch.as<uint32_t>(), st, d_task_len);
     // 3. accumulate + combine.  The payload of an entry is its position in the domain = [w][i] index;
     //    with tables that is the table index when n == b->n (checked by the callers).
@@ -128,9 +171,7 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
     // 16-bit windows has ~equal tasks already and skips it
     const uint32_t *order = nullptr;
     {
-        static int ord_env = -2;
-        if (ord_env == -2) { const char *e = getenv("ZK_TASK_ORDER"); ord_env = e ? atoi(e) : -1; }
-        bool want = ord_env >= 0 ? ord_env != 0 : (E / NB < 256);
+        bool want = E / NB < 256;
         if (want) {
             ZK_TRY(ctx->task_order.reserve(t_max * 4)); ZK_TRY(ctx->len_hist.reserve(2 * LEN_BINS * 4 + 64));
             uint32_t *gh = ctx->len_hist.as<uint32_t>(), *cur = gh + LEN_BINS;
@@ -142,17 +183,11 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
             order = ctx->task_order.as<uint32_t>();
         }
     }
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    if (ctx->prof_on) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, st); }
     {
-        static int minb = -1;          // experiment knob: ZK_ACC_MINB=2|3|4 (default chosen from measurements)
-        if (minb < 0) { const char *e = getenv("ZK_ACC_MINB"); minb = e ? atoi(e) : 3; }
         const Affine<F> *tb = cur_pts;
         const uint32_t *so = cur_sorted, *bo = cur_off, *to = ctx->task_off.as<uint32_t>();
         unsigned grid = (unsigned)((t_max + 127) / 128);
-        if (minb == 3) k_accumulate<F, 3><<<grid, 128, 0, st>>>(tb, so, bo, to, (uint32_t)NB, order, partials);
-        else if (minb == 4) k_accumulate<F, 4><<<grid, 128, 0, st>>>(tb, so, bo, to, (uint32_t)NB, order, partials);
-        else k_accumulate<F, 2><<<grid, 128, 0, st>>>(tb, so, bo, to, (uint32_t)NB, order, partials);
+        k_accumulate<F, 3><<<grid, 128, 0, st>>>(tb, so, bo, to, (uint32_t)NB, order, partials);      // 3 CTAs / SM (168 registers): measured best of 2 / 3 / 4
     }
     if (ctx->prof_on) { cudaEventRecord(ev1, st); ctx->prof_events.push_back(ev0); ctx->prof_events.push_back(ev1); }
     if (ctx->split_tail) {             // asynchronous MSM: combine / reduction continue on the high-priority tail stream

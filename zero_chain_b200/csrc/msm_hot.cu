@@ -2,7 +2,9 @@
 // inlined (ZK_HOT).  Everything else in the library calls them as functions (field.cuh, inlining policy).
 #define ZK_HOT 1
 #include "msm_driver.cuh"
+#ifdef ZK_EXPERIMENTS
 #include "field_wide.cuh"
+#endif
 
 using namespace zkmsm;
 
@@ -24,6 +26,7 @@ __global__ void k_bench_modmul(int iters, T *sink) {
     T r = a[0] + a[1] + a[2] + a[3];
     if (r.l[0] == 0x12345678u && r.l[1] == 0x9abcdef0u) sink[0] = r;   // keep the work alive
 }
+#ifdef ZK_EXPERIMENTS
 // experiment: separated multiply / reduce (field_wide.cuh) against the interleaved product, 4 chains per thread
 template <int MODE>
 __global__ void k_bench_wide(int iters, Fq *sink) {
@@ -45,13 +48,16 @@ __global__ void k_bench_wide(int iters, Fq *sink) {
     Fq r = a[0] + a[1] + a[2] + a[3];
     if (r.l[0] == 0x12345678u && r.l[1] == 0x9abcdef0u) sink[0] = r;
 }
+#endif
 void zk_launch_bench_modmul(int field, int blocks, int threads, int iters, void *sink, cudaStream_t st) {
     if (field == 0) k_bench_modmul<Fq><<<blocks, threads, 0, st>>>(iters, (Fq *)sink);
     else if (field == 1) k_bench_modmul<Fr><<<blocks, threads, 0, st>>>(iters, (Fr *)sink);
+#ifdef ZK_EXPERIMENTS
     else if (field == 10) k_bench_wide<0><<<blocks, threads, 0, st>>>(iters, (Fq *)sink);
     else if (field == 11) k_bench_wide<1><<<blocks, threads, 0, st>>>(iters, (Fq *)sink);
     else if (field == 12) k_bench_wide<2><<<blocks, threads, 0, st>>>(iters, (Fq *)sink);
     else if (field == 13) k_bench_wide<3><<<blocks, threads, 0, st>>>(iters, (Fq *)sink);
     else if (field == 14) k_bench_wide<4><<<blocks, threads, 0, st>>>(iters, (Fq *)sink);
     else k_bench_wide<5><<<blocks, threads, 0, st>>>(iters, (Fq *)sink);
+#endif
 }

@@ -340,8 +340,8 @@ extern "C" int zk_groth16_verify_batch_device(zk_ctx *ctx, const zk_pvk *k, size
     XYZZ<Fq> *part = ctx->v_part.as<XYZZ<Fq>>();
     // three independent strands, joined before the Miller loops: B decode + coefficients on the context's stream, A / C decode
     // and the public-input sums on the two auxiliary lanes (a small batch is latency-bound, so the strands overlap fully)
-    if (!ctx->aux) ZK_TRY(zk_ctx_create(ctx->device, nullptr, &ctx->aux));
-    if (!ctx->aux2) ZK_TRY(zk_ctx_create(ctx->device, nullptr, &ctx->aux2));
+    if (!ctx->aux) { ZK_TRY(zk_ctx_create(ctx->device, nullptr, &ctx->aux)); ctx->aux->opts = ctx->opts; }
+    if (!ctx->aux2) { ZK_TRY(zk_ctx_create(ctx->device, nullptr, &ctx->aux2)); ctx->aux2->opts = ctx->opts; }
     cudaStream_t s2 = ctx->aux->stream, s3 = ctx->aux2->stream;
     struct Events {                                                       // destroyed on every exit path
         cudaEvent_t e[3] = {nullptr, nullptr, nullptr};

@@ -68,6 +68,12 @@ class Context:
     def sync(self):
         _ck(_lib.lib().zk_ctx_sync(self._h))
 
+    OPT_AFFINE_MIN_ENTRIES, OPT_AFFINE_LEVELS = 1, 2
+
+    def set_opt(self, opt: int, value: int):
+        """zk_ctx_set_opt: tuning only (batched-affine threshold / rounds); results never depend on it."""
+        _ck(_lib.lib().zk_ctx_set_opt(self._h, opt, value))
+
     def profile(self, enable: bool):
         _ck(_lib.lib().zk_ctx_profile(self._h, int(enable)))
 
