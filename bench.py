@@ -42,11 +42,61 @@ ALGO_BYTES_PER_TERM = 128      # 96 B base + 32 B scalar
 
 
 def host_cores():
-    """CPUs this process may run on (the box's cgroup / affinity mask, not the machine's logical CPU count)."""
+    """Host threads for the CPU port: physical cores in the affinity mask, capped by the container's CPU quota."""
     try:
-        return len(os.sched_getaffinity(0))
+        cpus = os.sched_getaffinity(0)
     except Exception:
-        return os.cpu_count() or 1
+        cpus = set(range(os.cpu_count() or 1))
+    n = len(cpus)
+    try:        # physical cores among them: the port's OpenMP teams gain nothing from hyper-thread siblings and lose a lot in the short
+        seen, cur = set(), {}          # parallel regions of create_proof (measured on the B200 box: 128 threads 25x slower than 64)
+        for line in open("/proc/cpuinfo"):
+            if ":" in line:
+                k, v = [x.strip() for x in line.split(":", 1)]
+                cur[k] = v
+            elif cur:
+                if int(cur.get("processor", -1)) in cpus and "core id" in cur:
+                    seen.add((cur.get("physical id", "0"), cur["core id"]))
+                cur = {}
+        if seen:
+            n = min(n, len(seen))
+    except Exception:
+        pass
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            n = min(n, max(1, int(int(q) / int(p))))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read()); p = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, q // p))
+        except Exception:
+            pass
+    return n
+
+
+def pick_threads(co, trial):
+    """The CPU port is given the OpenMP team size it runs fastest with: `trial()` (a short sample of the workload) is timed at
+    the candidate counts (all usable CPUs, then halves) and the best one stays set.  Returns (threads, {threads: seconds})."""
+    top = host_cores()
+    try:
+        top = max(top, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    cands, c = [], top
+    while c >= 8 and len(cands) < 4:
+        cands.append(c); c //= 2
+    if not cands:
+        cands = [top]
+    seen = {}
+    for c in cands:
+        co.set_num_threads(c)
+        trial()                                   # warm-up at this team size
+        t = time.perf_counter(); trial(); seen[c] = time.perf_counter() - t
+    best = min(seen, key=seen.get)
+    co.set_num_threads(best)
+    return best, {str(k): round(v, 4) for k, v in seen.items()}
 
 
 def env_int(name, default):
@@ -483,6 +533,7 @@ def run_ours(args):
         from oracle import coracle as co
         co.set_num_threads(host_cores())
         bl = co.g1_fixed_base(base_scalars)           # the same bases, made by the oracle's own fixed-base code
+        _, tried = pick_threads(co, lambda: co.g1_msm(bl[:1 << 17], h_sets[last_set][:1 << 17]))
         t = time.time()
         want = co.g1_msm(bl, h_sets[last_set])
         dt = time.time() - t
@@ -491,7 +542,7 @@ def run_ours(args):
                         "threads_busy": "<= %d (bellman's multiexp runs one task per window, c = ceil(ln n))" % (255 // 14 + 1),
                         "sample": "one full 2^%d-term MSM (same bases and scalars as the last timed GPU step), oracle/zk_oracle.c "
                                   "bellman-style Pippenger, %.2f s" % (args.log_n, dt),
-                        "matches_gpu_result": bool(ok)}
+                        "matches_gpu_result": bool(ok), "threads_tried_s": tried}
         del bl
         if not ok:
             raise SystemExit("PARITY FAILURE: GPU MSM result differs from the oracle")
@@ -700,11 +751,10 @@ def prove_metrics(ctx, zk, sy, args, batch=256, steps=3, cpu=True, procs=None):
     cpu_block = None
     if cpu:
         from oracle import coracle as co
-        co.set_num_threads(host_cores())
         op = co.Params(crs.params_bytes, checked=False)
         n_cpu = min(8, batch)
         to_int = lambda row: sum(int(x) << (64 * i) for i, x in enumerate(row))
-        op.prove(*[v[0] for v in views], *dens, to_int(rs[0]), to_int(ss[0]))          # warm-up
+        _, tried = pick_threads(co, lambda: op.prove(*[v[0] for v in views], *dens, to_int(rs[0]), to_int(ss[0])))
         t = time.perf_counter()
         cpu_proofs = [op.prove(*[v[k] for v in views], *dens, to_int(rs[k]), to_int(ss[k])) for k in range(n_cpu)]
         cpu_dt = (time.perf_counter() - t) / n_cpu
@@ -712,7 +762,7 @@ def prove_metrics(ctx, zk, sy, args, batch=256, steps=3, cpu=True, procs=None):
             raise SystemExit("PARITY FAILURE: GPU proof bytes differ from the oracle")
         cpu_block = {"value": 1.0 / cpu_dt, "unit": "proofs/s", "cores": co.num_threads(), "kind": "port",
                      "sample": "oracle create_proof on the first %d witnesses of the batch, one after the other, same CRS" % n_cpu,
-                     "matches_gpu_proof_bytes": True}
+                     "matches_gpu_proof_bytes": True, "threads_tried_s": tried}
     params.free()
     try:
         verify_block = verify_metrics(ctx, zk, crs.params_bytes, proofs, np.ascontiguousarray(views[3][:, 1:, :]), cpu)
@@ -809,8 +859,7 @@ def run_reference(args):
     from oracle import coracle as co
     from zero_chain_b200 import synthetic as sy
     co.build()
-    cores = host_cores()
-    co.set_num_threads(cores)              # torchrun exports OMP_NUM_THREADS=1: the baseline is "all host threads", set explicitly
+    co.set_num_threads(host_cores())       # torchrun exports OMP_NUM_THREADS=1: the team size is set explicitly, never taken from the environment
     n = (1 << args.log_n) * max(1, args.gpus)
     bs = sy.random_fr_limbs(n, 7)
     bs[:, 1:] = 0                          # bases b_i * G with 64-bit b_i: 4x cheaper to generate on the CPU; the cost of an MSM does not depend on them
@@ -818,6 +867,7 @@ def run_reference(args):
     bases = co.g1_fixed_base(bs)
     setup_s = time.time() - t0
     sets = [sy.random_fr_limbs(n, 1000 + k) for k in range(2)]
+    cores, tried = pick_threads(co, lambda: co.g1_msm(bases[:1 << 17], sets[0][:1 << 17]))
     t0 = time.time()
     co.g1_msm(bases, sets[0])              # first warm-up step, also sizes the run
     t1 = time.time() - t0
@@ -839,20 +889,20 @@ def run_reference(args):
             "vs_baseline": None, "dtype": "u64-limb Montgomery, integer", "data": "synthetic",
             "config": {"workload": "G1 Pippenger MSM, 2^%d bases per GPU x %d = %d terms in one MSM on the host CPU (bellman multiexp restatement, "
                                    "c = ceil(ln n) = %d, one task per window)" % (args.log_n, max(1, args.gpus), n, c_win),
-                       "threads": cores, "threads_busy": "<= %d (one task per window, as bellman's multiexp schedules it)" % busy,
+                       "threads": cores, "threads_tried_s": tried, "threads_busy": "<= %d (one task per window, as bellman's multiexp schedules it)" % busy,
                        "setup_s_untimed": round(setup_s, 2)},
             "cpu_baseline": {"value": value, "unit": "Mop/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "Mop/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     if args.secondary:
         try:
-            line["secondary"] = {"groth16": reference_prove_metrics(co, sy, cores)}
+            line["secondary"] = {"groth16": reference_prove_metrics(co, sy)}
         except Exception as e:
             line["secondary"] = {"error": repr(e)}
     print(json.dumps(line), flush=True)
 
 
-def reference_prove_metrics(co, sy, cores):
+def reference_prove_metrics(co, sy):
     """proofs/sec of the CPU restatement of create_proof on the confidential_transfer-shaped synthetic circuit (same R1CS, toy CRS
     seeds and witness seeds as our arm's secondary.groth16), all host threads, one proof after the other (zface proves one at a time)."""
     r1cs = sy.make_r1cs(seed=1, **sy.CONF_SHAPE)
@@ -861,13 +911,14 @@ def reference_prove_metrics(co, sy, cores):
     op = co.Params(crs.params_bytes, checked=False)
     _wk_init(crs)
     wit = [_wk_witness(k) for k in range(4)]
-    op.prove(*wit[0][1], *dens, wit[0][2], wit[0][3])
+    cores, tried = pick_threads(co, lambda: op.prove(*wit[0][1], *dens, wit[0][2], wit[0][3]))
     t = time.perf_counter()
     out = [op.prove(*w[1], *dens, w[2], w[3]) for w in wit]
     dt = (time.perf_counter() - t) / len(wit)
     ok = all(o == w[4] for o, w in zip(out, wit))
     return {"metric": "proofs_per_sec (confidential_transfer shape: 19974 constraints, 23 inputs, domain 2^15; synthetic R1CS, toy CRS)",
-            "e2e_proofs_per_sec": 1.0 / dt, "ms_per_proof": dt * 1e3, "cores": cores, "proofs": len(wit), "matches_closed_form": bool(ok)}
+            "e2e_proofs_per_sec": 1.0 / dt, "ms_per_proof": dt * 1e3, "cores": cores, "threads_tried_s": tried, "proofs": len(wit),
+            "matches_closed_form": bool(ok)}
 
 
 def main():

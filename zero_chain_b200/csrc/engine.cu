@@ -191,12 +191,12 @@ extern "C" int zk_msm(zk_ctx *ctx, const zk_bases *b, const uint64_t *scalars, s
     ZK_CUDA(cudaMemcpyAsync(ctx->scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
     return zk_msm_device(ctx, b, ctx->scalars.p, n, out);
 }
+// one warp: out = sum of the n partial sums, each addition warp-cooperative (curve_coop.cuh)
 template <class F>
-__global__ void k_fold_serial(const XYZZ<F> *in, int n, XYZZ<F> *out) {
-    if (threadIdx.x | blockIdx.x) return;
+__global__ void __launch_bounds__(32) k_fold_serial(const XYZZ<F> *in, int n, XYZZ<F> *out) {
     XYZZ<F> r = in[0];
-    for (int i = 1; i < n; i++) r.add(in[i]);
-    out[0] = r;
+    for (int i = 1; i < n; i++) zkcoop::add(r, in[i]);
+    if (threadIdx.x == 0) out[0] = r;
 }
 // ---- asynchronous MSM: bellman's multiexp returns a future (multiexp.rs); begin / end is that future on CUDA streams ----
 static const size_t PARTIAL_IN_FLIGHT = ~(size_t)0;      // pending_bytes sentinel: a partial MSM is in flight, no host result yet

@@ -18,6 +18,7 @@
 #include <stdlib.h>
 #include "internal.h"
 #include "codec.cuh"
+#include "curve_coop.cuh"
 
 struct zk_params {
     int device = 0;
@@ -335,10 +336,10 @@ __global__ void __launch_bounds__(SCALE_T) k_scale_points(const G1XYZZ *__restri
     int top = -1;
     for (int i = 7; i >= 0 && top < 0; i--) if (k[i]) top = 32 * i + 31 - __clz(k[i]);
     if (top > 254) top = 254;          // a non-canonical r / s (>= 2^255) is reported through the error flag by k_blinding_terms; stay inside pw[]
-    if (t == 0) {
+    if (t < 32) {                                                               // warp 0: the doubling chain, three cooperative stages per doubling
         G1XYZZ d = j ? gb1[b] : ga[b];
-        pw[0] = d;
-        for (int i = 1; i <= top; i++) { d = d.dbl(); pw[i] = d; }
+        if (t == 0) pw[0] = d;
+        for (int i = 1; i <= top; i++) { zkcoop::dbl(d); if (t == 0) pw[i] = d; }
     }
     __syncthreads();
     G1XYZZ acc = G1XYZZ::inf();

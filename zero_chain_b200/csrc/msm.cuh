@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "curve.cuh"
+#include "curve_coop.cuh"
 #include "msm_accum.cuh"
 #include "tma.cuh"
 
@@ -508,27 +509,27 @@ __global__ void __launch_bounds__(RED_T) k_seg_sums(const XYZZ<F> *__restrict__ 
     for (int j = k * L; j < j1; j++) acc.add(p[j]);
     out[id] = acc;
 }
-// thread per domain: R = 2^s * Rrc[2 dom] + Rrc[2 dom + 1]
+// WARP per domain: R = 2^s * Rrc[2 dom] + Rrc[2 dom + 1]; the s doublings and the addition run warp-cooperatively (curve_coop.cuh)
 template <class F>
-__global__ void k_join_rowcol(const XYZZ<F> *__restrict__ Rrc, int s, int n_dom, XYZZ<F> *__restrict__ R) {
-    int dom = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) k_join_rowcol(const XYZZ<F> *__restrict__ Rrc, int s, int n_dom, XYZZ<F> *__restrict__ R) {
+    int dom = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (dom >= n_dom) return;
     XYZZ<F> r = Rrc[2 * dom];
-    for (int k = 0; k < s; k++) r = r.dbl();
-    r.add(Rrc[2 * dom + 1]);
-    R[dom] = r;
+    for (int k = 0; k < s; k++) zkcoop::dbl(r);
+    zkcoop::add(r, Rrc[2 * dom + 1]);
+    if ((threadIdx.x & 31) == 0) R[dom] = r;
 }
 
-// single thread: out = sum_w 2^(c w) R[w]  (Horner over windows; ad-hoc MSM without tables)
+// one WARP: out = sum_w 2^(c w) R[w]  (Horner over windows; ad-hoc MSM without tables).  The (W - 1) c doublings are inherently
+// serial; each runs as three warp-cooperative stages instead of nine dependent products.
 template <class F>
-__global__ void k_horner_windows(const XYZZ<F> *__restrict__ R, int W, int c, XYZZ<F> *__restrict__ out) {
-    if (threadIdx.x | blockIdx.x) return;
+__global__ void __launch_bounds__(32) k_horner_windows(const XYZZ<F> *__restrict__ R, int W, int c, XYZZ<F> *__restrict__ out) {
     XYZZ<F> r = R[W - 1];
     for (int w = W - 2; w >= 0; w--) {
-        for (int k = 0; k < c; k++) r = r.dbl();
-        r.add(R[w]);
+        for (int k = 0; k < c; k++) zkcoop::dbl(r);
+        zkcoop::add(r, R[w]);
     }
-    out[0] = r;
+    if (threadIdx.x == 0) out[0] = r;
 }
 
 // ---- precomputed tables: tbl[w][i] = 2^(c w) P_i (affine), w = 0..W-1 -------------------------------

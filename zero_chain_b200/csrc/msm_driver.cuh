@@ -216,13 +216,15 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
         k_sum_points<F><<<(unsigned)((n_g * 32 + RED_T - 1) / RED_T), RED_T, sm_warp, st>>>(part, slices, (int)n_g, X);
         k_finish_bits<F><<<(unsigned)((nd * 32 + RED_T - 1) / RED_T), RED_T, sm_warp, st>>>(X, bits, (int)nd, out);
     };
-    if (tables && ((n_dom >= 8 && c >= 7) || c > 16)) {
+    XYZZ<F> *Rdom = tables ? R : R + 1;      // per-domain results; without tables they are the window sums the Horner pass folds into R[0]
+    if ((n_dom >= 8 && c >= 7) || (tables && c > 16)) {
         // two-level row/column scheme, 2 additions per bucket (msm.cuh): many domains (batched proving) or wide windows
         const int s = (c - 1) / 2, nr = nbins >> s, nc = (1 << s) - 1;
         ZK_TRY(ctx->red_rows.reserve(2 * n_dom * (size_t)nr * pt));
-        ZK_TRY(ctx->result.reserve((3 * n_dom + batch + 2) * pt));
+        ZK_TRY(ctx->result.reserve((3 * n_dom + batch + 4) * pt));
         R = ctx->result.as<XYZZ<F>>();
-        XYZZ<F> *rc = ctx->red_rows.as<XYZZ<F>>(), *Rrc = R + n_dom + 1;
+        Rdom = tables ? R : R + 1;
+        XYZZ<F> *rc = ctx->red_rows.as<XYZZ<F>>(), *Rrc = R + n_dom + 2;
         if (sm_warp > 48 * 1024) {
             ZK_CUDA(cudaFuncSetAttribute(k_rowcol_sums<F, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_warp));
         }
@@ -244,13 +246,11 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
             k_seg_sums<F><<<(unsigned)((n_slots + RED_T - 1) / RED_T), RED_T, 0, st>>>(t2, n_slots, P2, P2, 1, rc);
         }
         bit_reduce(rc, nr, c - s, 2 * n_dom, Rrc);      // rows: hi in [1, 2^(c-1-s)] (c-s bits); columns: lo in [1, 2^s - 1]
-        k_join_rowcol<F><<<(unsigned)((n_dom + 63) / 64), 64, 0, st>>>(Rrc, s, (int)n_dom, R);
-    } else if (tables) {
-        bit_reduce(buckets, nbins, n_bits, n_dom, R);
+        k_join_rowcol<F><<<(unsigned)((n_dom * 32 + 127) / 128), 128, 0, st>>>(Rrc, s, (int)n_dom, Rdom);
     } else {
-        bit_reduce(buckets, nbins, n_bits, n_dom, R + 1);
-        k_horner_windows<F><<<1, 32, 0, st>>>(R + 1, W, c, R);
+        bit_reduce(buckets, nbins, n_bits, n_dom, Rdom);
     }
+    if (!tables) k_horner_windows<F><<<1, 32, 0, st>>>(Rdom, W, c, R);
     ZK_CUDA(cudaGetLastError());
     return ZK_OK;
 }
