@@ -11,7 +11,7 @@ if what.startswith("msm"):
     logn = int(what[3:])
     n = 1 << logn
     bases = zk.scalar_mul_many(ctx, 1, zk.G1_GENERATOR, sy.random_fr_limbs(n, 1))
-    b = zk.Bases(ctx, 1, bases, window_bits=int(__import__("os").environ.get("ZK_WB", 0)), precompute=True)
+    b = zk.Bases(ctx, 1, bases, window_bits=int(__import__("os").environ.get("ZK_WB", 0)), precompute=len(sys.argv) < 3 or sys.argv[2] != "fresh")
     d = torch.from_numpy(sy.random_fr_limbs(n, 2).view(np.int64)).cuda()
     torch.cuda.synchronize()
     for _ in range(3):
