@@ -60,9 +60,12 @@ int zk_ctx_sync(zk_ctx *ctx);
  *                              rounds (6 field products per addition instead of 10, one shared inversion per round, ~0.15 ms of
  *                              latency each) before the XYZZ pass.  Default -1 = never: on B200 the rounds measured no faster
  *                              than the XYZZ pass alone (profiles/r02_experiments.md); 0 = always.
- *   ZK_OPT_AFFINE_LEVELS       number of rounds; -1 (default) = from the average bucket length. */
+ *   ZK_OPT_AFFINE_LEVELS       number of rounds; -1 (default) = from the average bucket length.
+ *   ZK_OPT_VERIFY_LANES        1 (default): the verifier's Miller loops and final exponentiations spread every Fq12 value over six
+ *                              lanes of a warp; 0: one thread per proof (the round-1 kernels, kept as the A/B reference). */
 #define ZK_OPT_AFFINE_MIN_ENTRIES 1
 #define ZK_OPT_AFFINE_LEVELS 2
+#define ZK_OPT_VERIFY_LANES 3
 int zk_ctx_set_opt(zk_ctx *ctx, int opt, long value);
 void *zk_ctx_stream(zk_ctx *ctx);
 

@@ -7,6 +7,9 @@ from oracle import coracle as co
 from zero_chain_b200 import groth16 as zk
 from zero_chain_b200 import synthetic as sy
 ctx = zk.Context(0)
+import os
+if os.environ.get("ZK_LANES") is not None:
+    ctx.set_opt(zk.Context.OPT_VERIFY_LANES, int(os.environ["ZK_LANES"]))
 r1cs = sy.make_r1cs(seed=1, n_constraints=60, n_inputs=23, n_aux=50, a_aux_density=40, b_density=33)
 crs = sy.make_toy_crs(r1cs, co.g1_fixed_base, co.g2_fixed_base, seed=2)
 params = zk.Parameters.read(ctx, crs.params_bytes, checked=True)

@@ -67,6 +67,7 @@ extern "C" int zk_ctx_set_opt(zk_ctx *c, int opt, long value) {
         if (!x) continue;
         if (opt == ZK_OPT_AFFINE_MIN_ENTRIES) x->opts.ba_min_entries = value;
         else if (opt == ZK_OPT_AFFINE_LEVELS) x->opts.ba_levels = value;
+        else if (opt == ZK_OPT_VERIFY_LANES) x->opts.verify_lanes = value;
         else { zk_set_error("zk_ctx_set_opt: unknown option %d", opt); return ZK_ERR_INVALID; }
     }
     return ZK_OK;

@@ -68,7 +68,7 @@ class Context:
     def sync(self):
         _ck(_lib.lib().zk_ctx_sync(self._h))
 
-    OPT_AFFINE_MIN_ENTRIES, OPT_AFFINE_LEVELS = 1, 2
+    OPT_AFFINE_MIN_ENTRIES, OPT_AFFINE_LEVELS, OPT_VERIFY_LANES = 1, 2, 3
 
     def set_opt(self, opt: int, value: int):
         """zk_ctx_set_opt: tuning only (batched-affine threshold / rounds); results never depend on it."""
