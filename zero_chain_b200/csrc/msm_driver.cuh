@@ -91,16 +91,17 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
     //     that follows wants ~3 points per bucket left.
     const Affine<F> *cur_pts = (const Affine<F> *)b->d_tbl;
     const uint32_t *cur_sorted = ctx->sorted.as<uint32_t>(), *cur_off = ctx->bucket_off.as<uint32_t>(), *cur_sizes = ctx->sizes.as<uint32_t>();
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    if (ctx->prof_on) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, st); }
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;      // zk_ctx_profile: the bucket-accumulation stage (affine rounds, if any, + the XYZZ pass)
     {
         int levels = 0;
         if (ctx->opts.ba_min_entries >= 0 && (long)E >= ctx->opts.ba_min_entries) {      // a round costs ~0.1 ms of latency (its inversion): small MSMs stay on the XYZZ pass alone
             if (ctx->opts.ba_levels >= 0) levels = (int)(ctx->opts.ba_levels < BA_MAX_LEVELS ? ctx->opts.ba_levels : BA_MAX_LEVELS);
             else for (size_t avg = E / NB; avg >= 6 && levels < BA_MAX_LEVELS; avg >>= 1) levels++;
         }
+        if (ctx->prof_on && levels > 0) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, st); }
         size_t in_max = E;
         int minb = BA_MINB, k_force = 0;
+        (void)minb;
 #ifdef ZK_EXPERIMENTS
         if (const char *e = getenv("ZK_BA_MINB")) minb = atoi(e);
         if (const char *e = getenv("ZK_BA_K")) k_force = atoi(e);
@@ -187,6 +188,7 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
         const Affine<F> *tb = cur_pts;
         const uint32_t *so = cur_sorted, *bo = cur_off, *to = ctx->task_off.as<uint32_t>();
         unsigned grid = (unsigned)((t_max + 127) / 128);
+        if (ctx->prof_on && !ev0) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, st); }
         k_accumulate<F, 3><<<grid, 128, 0, st>>>(tb, so, bo, to, (uint32_t)NB, order, partials);      // 3 CTAs / SM (168 registers): measured best of 2 / 3 / 4
     }
     if (ctx->prof_on) { cudaEventRecord(ev1, st); ctx->prof_events.push_back(ev0); ctx->prof_events.push_back(ev1); }
