@@ -85,6 +85,12 @@ def main():
     res["pairing_kat"] = {"alpha_g1_uncompressed": pk[0:96].hex(), "beta_g2_uncompressed": pk[192:384].hex(),
                           "alpha_g1_beta_g2_fq12": vk[0:576].hex(),
                           "source": "zface/params/conf_pk.dat[0:96], [192:384]; zface/params/conf_vk.dat[0:576]"}
+    # a well-formed 192-byte proof held by the reference's own test (core/primitives/src/proof.rs:86-98): Proof::read must accept
+    # it (flags, x < q, square roots, sign bits, subgroup membership of A, B, C) and Proof::write must give the same bytes back
+    src = open(os.path.join(REF, "core/primitives/src/proof.rs")).read()
+    m = re.search(r'fn test_proof_into_from\(\).*?hex!\("([0-9a-f]{384})"\)', src, re.S)
+    assert m
+    res["proof_kat"] = {"proof_hex": m.group(1), "source": "core/primitives/src/proof.rs:89 (test_proof_into_from)"}
     # verifier fixtures (binary, small): the shipped PreparedVerifyingKey files and the VerifyingKey head of the matching
     # proving keys (Parameters::write starts with vk: 868 bytes + 96 per ic point).  prepare_verifying_key of the latter
     # must reproduce the former byte for byte (tests/test_oracle_pairing.py, tests/test_gpu_verify.py).

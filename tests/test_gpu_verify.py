@@ -217,3 +217,22 @@ def test_verify_key_without_public_inputs(ctx):
         zk.verify_proofs(pvk, proof, [[1]])
     assert e.value.code == -9
     pvk.free(); params.free()
+
+
+def test_reference_literal_proof_is_read_by_the_device(ctx):
+    """The reference's own 192-byte proof literal (core/primitives/src/proof.rs:89): three points this repository did not make go
+    through the device Proof::read (square roots, sign bits, subgroup tests) and the pairing check under the shipped key; the
+    verdict must be the oracle's (a proper `false`: read succeeded, the proof belongs to other inputs)."""
+    import json
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    raw = bytes.fromhex(json.load(open(os.path.join(gold, "kats.json")))["proof_kat"]["proof_hex"])
+    pvk = zk.PreparedVerifyingKey.read(ctx, open(os.path.join(gold, "conf_pvk.dat"), "rb").read())
+    opvk = co.PreparedVerifyingKey.read(open(os.path.join(gold, "conf_pvk.dat"), "rb").read())
+    inputs = list(range(1, 23))
+    bad_flag = bytes([raw[0] & 0x7f]) + raw[1:]
+    minus_a = bytes([raw[0] ^ 0x20]) + raw[1:]
+    batch = raw + bad_flag + minus_a + raw
+    got = zk.verify_proofs(pvk, batch, [inputs] * 4)
+    want = opvk.verify_batch(batch, co.ints_to_limbs(inputs * 4, 4), 22)
+    assert got == want == [0, 2, 0, 0]
+    pvk.free()

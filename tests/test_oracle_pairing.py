@@ -168,3 +168,25 @@ def test_c_oracle_verifier_agrees_with_pyref():
         q = pr.ec_mul(pr.FQ2, pr.G2_GEN, kk)
         pp = pr.proof_bytes(pr.ec_mul(pr.FQ, pr.G1_GEN, kk), q, pr.G1_GEN)
         assert k.verify_batch(pp, co.ints_to_limbs(inputs[0], 4), 2) == [0]
+
+
+def test_reference_literal_proof_reads_and_writes_back():
+    """The 192-byte proof the reference's own test holds (core/primitives/src/proof.rs:86-98, test_proof_into_from): Proof::read
+    accepts it and Proof::write returns the same bytes — in both oracles; and the SCALE wrapper round-trips it."""
+    import json, os
+    K = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kats.json")))
+    raw = bytes.fromhex(K["proof_kat"]["proof_hex"])
+    assert len(raw) == 192
+    a, b, c = pr.proof_read(raw)                                   # big-integer oracle: decompression, sign bits, r-torsion of A, B, C
+    assert pr.proof_bytes(a, b, c) == raw
+    from zero_chain_b200 import groth16 as zk
+    w = zk.Proof.from_slice(raw)
+    enc = w.encode()
+    assert enc[:2] == bytes([0x01, 0x03]) and len(enc) == 194       # compact(192) = (192 << 2) | 1 little-endian
+    assert zk.Proof.decode(enc) == w and zk.Proof.decode(enc).as_bytes() == raw and str(w) == "0x" + raw.hex()
+    # C oracle: verdict must be a proper boolean (Proof::read succeeded), never InvalidData / PointInfinity
+    vk = open(os.path.join(os.path.dirname(__file__), "golden", "conf_vk_head.bin"), "rb").read()
+    k = co.PreparedVerifyingKey.prepare(vk)
+    inputs = co.ints_to_limbs(list(range(1, 23)), 4)
+    assert k.verify_batch(raw, inputs, 22) == [0]
+    assert k.verify_batch(bytes([raw[0] & 0x7f]) + raw[1:], inputs, 22) == [2]

@@ -345,6 +345,56 @@ def pairing(ctx: Context, g1_uncompressed: bytes, g2_uncompressed: bytes) -> byt
     return out[:576 * n].tobytes()
 
 
+class Proof:
+    """zerochain_primitives::Proof(Vec<u8>) — the wire wrapper of the 192 proof bytes (core/primitives/src/proof.rs:12-62): the
+    runtime moves `Proof` SCALE-encoded (parity_codec derive: Compact<u32> length, then the bytes) and converts to / from
+    bellman_verifier::Proof with Proof::read / Proof::write.  Pure byte handling: nothing here touches the device."""
+    SIZE = 192
+
+    def __init__(self, raw: bytes):
+        self._b = bytes(raw)
+
+    @staticmethod
+    def from_slice(raw: bytes) -> "Proof":
+        return Proof(raw)
+
+    def as_bytes(self) -> bytes:
+        return self._b
+
+    def encode(self) -> bytes:
+        """parity_codec::Encode of Vec<u8>: compact length prefix (single / two / four-byte mode), then the bytes."""
+        n = len(self._b)
+        if n < 1 << 6:
+            pre = bytes([n << 2])
+        elif n < 1 << 14:
+            pre = ((n << 2) | 1).to_bytes(2, "little")
+        else:
+            assert n < 1 << 30
+            pre = ((n << 2) | 2).to_bytes(4, "little")
+        return pre + self._b
+
+    @staticmethod
+    def decode(buf: bytes) -> "Proof":
+        mode = buf[0] & 3
+        if mode == 0:
+            n, off = buf[0] >> 2, 1
+        elif mode == 1:
+            n, off = int.from_bytes(buf[:2], "little") >> 2, 2
+        elif mode == 2:
+            n, off = int.from_bytes(buf[:4], "little") >> 2, 4
+        else:
+            raise ValueError("big-integer compact lengths do not occur for proofs")
+        if len(buf) < off + n:
+            raise ValueError("truncated Proof")
+        return Proof(buf[off:off + n])
+
+    def __eq__(self, other):
+        return isinstance(other, Proof) and self._b == other._b
+
+    def __str__(self):
+        return "0x" + self._b.hex()
+
+
 class ProvingAssignment:
     """What bellman's ProvingAssignment holds after `circuit.synthesize` and the input rows
     (SURVEY.md §3.2): per-constraint evaluations, assignments and the three density maps."""
