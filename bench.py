@@ -32,10 +32,11 @@ sys.path.insert(0, ROOT)
 
 LOG_N = 20
 N_SETS = 8                     # distinct scalar vectors cycled through: 8 x 32 MiB = 256 MiB > 126 MB L2
-KERNELS_PER_MSM = 24           # 20-bit windows at 2^20: digits, tile_hist, col_scan, 3 x scan_block, scan_add, scatter, fine_sort,
-                               # pick_task_len, len_hist, len_scan, len_place, accumulate, combine_serial, combine_warp,
-                               # rowcol_stage1, 2 x seg_sums, bit_sums, sum_points, finish_bits, join_rowcol, encode_xyzz
-                               # (counted from the ncu launch list profiles/r01_launches_msm_2p20.csv; N > 1 adds the fold kernel)
+KERNELS_PER_MSM = 38           # 20-bit windows at 2^20: digits, tile_hist, col_scan, scan_block, scatter, fine_sort; 2 batched-affine rounds x
+                               # (half_sizes, 2 x scan_block, scan_add, ba_forward, ba_invert, ba_backward); pick_task_len, 2 x scan_block,
+                               # scan_add, len_hist, len_scan, len_place, accumulate, combine_serial, combine_warp, rowcol_stage1, 2 x seg_sums,
+                               # bit_sums, sum_points, finish_bits, join_rowcol, encode_xyzz
+                               # (counted from the ncu launch list profiles/r02_launches_msm_2p20.csv; N > 1 adds the fold kernel)
 ALGO_MODMUL_PER_TERM = 176     # 11 (mixed add) x ceil(255/16) windows — the FIXED convention of SURVEY.md §8(d) / BASELINE.md §3,
                                # independent of the window size the library actually uses
 ALGO_BYTES_PER_TERM = 128      # 96 B base + 32 B scalar
@@ -307,11 +308,13 @@ class MsmJob:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    def timed(self, fn, steps, warmup):
+    def timed(self, fn, steps, warmup, profile=False):
         torch = self.torch
         for k in range(warmup):
             fn(k)
         self.barrier()
+        if profile:
+            self.ctx.profile(True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(self.stream)
         last = None
@@ -319,7 +322,12 @@ class MsmJob:
             last = fn(warmup + k)
         e1.record(self.stream)
         self.barrier()
-        return self._max_over_ranks(e0.elapsed_time(e1)), last
+        ms = self._max_over_ranks(e0.elapsed_time(e1))
+        if profile:
+            a, ca = self.ctx.profile_read(), self.ctx.profile_counts()
+            self.ctx.profile(False)
+            return ms, last, (a[0], a[1], ca[0], ca[2])
+        return ms, last
 
     def timed_pipelined(self, begin, steps, warmup, profile=False):
         """successive MSMs are independent jobs and the reference's multiexp returns a future: two of them are kept in flight on
@@ -353,7 +361,7 @@ class MsmJob:
         if profile:
             a, b_ = self.ctx.profile_read(), self.ctx2.profile_read()
             ca, cb = self.ctx.profile_counts(), self.ctx2.profile_counts()
-            prof = (a[0] + b_[0], a[1] + b_[1], ca[0] + cb[0])
+            prof = (a[0] + b_[0], a[1] + b_[1], ca[0] + cb[0], ca[2] + cb[2])
             self.ctx.profile(False); self.ctx2.profile(False)
         return ms, res[warmup + steps - 1], prof
 
@@ -447,6 +455,10 @@ def run_ours(args):
             os.close(saved)
     n = 1 << args.log_n
     ctx, ctx2 = zk.Context(local), zk.Context(local)
+    if args.affine_min_entries is not None:           # measurement switch: batched-affine bucket rounds (default: library default = off)
+        for c in (ctx, ctx2):
+            c.set_opt(zk.Context.OPT_AFFINE_MIN_ENTRIES, args.affine_min_entries)
+            c.set_opt(zk.Context.OPT_AFFINE_LEVELS, args.affine_levels)
 
     # ---- setup (untimed): this rank's shard of the bases, generated on the device, + window tables ----
     t0 = time.time()
@@ -462,10 +474,12 @@ def run_ours(args):
 
     sampler = ClockSampler(local) if rank == 0 else None
     W = max(4, args.warmup)            # the last timed step (W + steps - 1) picks the scalar set the checks use
-    ms_dev, res_dev, prof = job.timed_pipelined(job.begin_device, args.steps, W, profile=True)
+    ms_dev, res_dev, _ = job.timed_pipelined(job.begin_device, args.steps, W)
     clocks = sampler.stop() if sampler else None
     ms_e2e, res_e2e, _ = job.timed_pipelined(job.begin_e2e, args.steps, W)
-    ms_b, res_b = job.timed(job.step_device, args.steps, W)
+    # the dominant stage is timed (CUDA events on the launching stream, zk_ctx_profile) during the BLOCKING loop: with two MSMs in
+    # flight the interval between two events on one stream also contains the other context's kernels
+    ms_b, res_b, prof = job.timed(job.step_device, args.steps, W, profile=True)
     ms_be, res_be = job.timed(job.step_e2e, args.steps, W)
     if not (res_b == res_dev == res_be == res_e2e):
         raise SystemExit("PARITY FAILURE: pipelined / blocking / host-buffer MSM results differ")
@@ -501,12 +515,15 @@ def run_ours(args):
     value = total_terms * args.steps / (ms_dev * 1e-3) / 1e6
     e2e_value = total_terms * args.steps / (ms_e2e * 1e-3) / 1e6
     hbm_peak, hbm_how = peaks()
-    acc_ms, acc_launches, acc_adds = prof
+    acc_ms, acc_launches, acc_adds, acc_xyzz = prof
     acc_avg_s = acc_ms * 1e-3 / max(1, acc_launches)
     algo_modmul = ALGO_MODMUL_PER_TERM * n            # per launch: one launch processes one rank's n terms
-    exec_modmul = 10.0 * acc_adds / max(1, acc_launches)   # bucket additions counted on the device x 10 products (XYZZ mixed addition)
+    # bucket additions counted on the device: 10 products for those the XYZZ pass does, 6.4 for those of the batched-affine rounds
+    # (6 per addition + the warp scans of the thread totals: 13 products per 32 additions)
+    exec_modmul = (10.0 * acc_xyzz + 6.4 * (acc_adds - acc_xyzz)) / max(1, acc_launches)
     roofline = {
-        "kernel": "zkmsm::k_accumulate<Fq> (bucket accumulation)",
+        "kernel": "bucket accumulation stage: zkmsm::k_ba_forward / k_ba_invert / k_ba_backward rounds + zkmsm::k_accumulate<Fq>",
+        "additions_per_launch": {"total": acc_adds / max(1, acc_launches), "xyzz_pass": acc_xyzz / max(1, acc_launches)},
         "bound": "int32-modmul",                       # IMAD issue rate, not HBM, not tensor
         # LEAD figure: products the kernel actually executes / time / calibrated peak = efficiency of the integer-multiply pipe
         "executed_frac": exec_modmul / acc_avg_s / modmul_peak,
@@ -514,10 +531,12 @@ def run_ours(args):
         "achieved": algo_modmul / acc_avg_s, "peak": modmul_peak, "unit": "Fq-modmul/s",
         "frac": algo_modmul / acc_avg_s / modmul_peak,
         "peak_how": "zk_bench_modmul: register-resident independent Fq Montgomery products, measured in this run",
-        "avg_launch_ms": acc_avg_s * 1e3, "launches": acc_launches, "share_of_step": acc_ms / ms_dev,
+        "avg_launch_ms": acc_avg_s * 1e3, "launches": acc_launches, "share_of_step": acc_ms / ms_b,
+        "timed_in": "the blocking-call loop (one MSM at a time): CUDA events on the launching stream around the stage, incl. the ~0.2 ms serial inversion of each batched-affine round",
         "note": "frac uses SURVEY 8(d)'s FIXED algorithmic count (176 products per term = 11 x 16 windows) and can exceed 1 because "
-                "the kernel executes fewer (10 per mixed addition x %d table rows per term, %d-bit windows); executed_frac counts the "
-                "additions really performed (device counter) and is the pipe efficiency" % (255 // bases.window_bits + 1, bases.window_bits),
+                "the stage executes fewer (%d table rows per term with %d-bit windows; 10 products per XYZZ mixed addition, 6.4 per "
+                "batched-affine addition); executed_frac counts the additions really performed (device counters) and is the pipe efficiency"
+                % (255 // bases.window_bits + 1, bases.window_bits),
         "whole_msm_frac": ALGO_MODMUL_PER_TERM * total_terms * args.steps / (ms_dev * 1e-3) / (modmul_peak * world),
         "hbm": {"bound": "hbm", "achieved": ALGO_BYTES_PER_TERM * n / acc_avg_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": ALGO_BYTES_PER_TERM * n / acc_avg_s / 1e9 / hbm_peak, "peak_how": hbm_how},
@@ -674,7 +693,7 @@ def g2_msm_metrics(ctx, zk, sy, torch):
         e1.record(stream)
         ctx.sync(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
-        _, g2_adds = ctx.profile_counts()
+        _, g2_adds, _, g2_xyzz = ctx.profile_counts()
         ctx.profile(False)
         other = zk.Bases(ctx, 2, bl, window_bits=max(4, b.window_bits - 3), precompute=True)
         same = zk.multiexp_device(other, d.data_ptr(), n, batch) == got == ref
@@ -684,10 +703,10 @@ def g2_msm_metrics(ctx, zk, sy, torch):
         terms = n * batch
         out[tag] = {"terms": terms, "ms": ms, "mops": terms / ms / 1e3, "window_bits": b.window_bits,
                     "frac": 528.0 * terms / (ms * 1e-3) / fq_peak,
-                    "executed_frac": 28.0 * g2_adds / reps / (ms * 1e-3) / fq_peak,
-                    "executed_modmul": 28.0 * g2_adds / reps, "consistent_across_window_sizes": True}
+                    "executed_frac": (28.0 * g2_xyzz + 17.6 * (g2_adds - g2_xyzz)) / reps / (ms * 1e-3) / fq_peak,
+                    "executed_modmul": (28.0 * g2_xyzz + 17.6 * (g2_adds - g2_xyzz)) / reps, "consistent_across_window_sizes": True}
     out["unit"] = "Fq-modmul/s against the calibrated Fq peak"; out["peak"] = fq_peak
-    out["note"] = "frac: SURVEY 8(d) convention 528 n; executed_frac: 28 Fq products per G2 bucket addition (8 Fq2 products + 2 Fq2 squarings) x additions counted on the device, bucket reduction not counted"
+    out["note"] = "frac: SURVEY 8(d) convention 528 n; executed_frac: 28 Fq products per G2 XYZZ addition (8 Fq2 products + 2 squarings), 17.6 per batched-affine one, x additions counted on the device; bucket reduction not counted"
     return out
 
 
@@ -720,7 +739,7 @@ def prove_metrics(ctx, zk, sy, args, batch=256, steps=3, cpu=True, procs=None):
     for _ in range(steps):
         proofs = zk.create_proof_batch_raw(params, batch, *views, *dens, rs, ss)
     dt = (time.perf_counter() - t) / steps
-    g1_adds, g2_adds = ctx.profile_counts()
+    g1_adds, g2_adds, g1_xyzz, g2_xyzz = ctx.profile_counts()
     acc_ms, acc_launches = ctx.profile_read()
     ctx.profile(False)
     bad = [k for k in range(batch) if proofs[192 * k:192 * (k + 1)] != want_all[192 * k:192 * (k + 1)]]
@@ -731,15 +750,17 @@ def prove_metrics(ctx, zk, sy, args, batch=256, steps=3, cpu=True, procs=None):
     fr_peak, _ = zk.bench_modmul(ctx, zk.FIELD_FR, 148 * 4, 256, 3000)
     log_m = 15
     ntt_fr = 7 * (1 << (log_m - 1)) * log_m                                   # 7 transforms of 2^15 per proof, (m/2) log m butterflies each
-    per_proof = {"g1_bucket_additions": g1_adds / (steps * batch), "g2_bucket_additions": g2_adds / (steps * batch), "ntt_fr_modmul": ntt_fr}
-    exec_fq = 10.0 * per_proof["g1_bucket_additions"] + 28.0 * per_proof["g2_bucket_additions"] + ntt_fr * fq_peak / fr_peak
+    per_proof = {"g1_bucket_additions": g1_adds / (steps * batch), "g2_bucket_additions": g2_adds / (steps * batch),
+                 "g1_left_to_xyzz_pass": g1_xyzz / (steps * batch), "g2_left_to_xyzz_pass": g2_xyzz / (steps * batch), "ntt_fr_modmul": ntt_fr}
+    g1a, g1x, g2a, g2x = (per_proof[k] for k in ("g1_bucket_additions", "g1_left_to_xyzz_pass", "g2_bucket_additions", "g2_left_to_xyzz_pass"))
+    exec_fq = 10.0 * g1x + 6.4 * (g1a - g1x) + 28.0 * g2x + 17.6 * (g2a - g2x) + ntt_fr * fq_peak / fr_peak
     algo_fq = 176.0 * 80722 + 528.0 * 12402 + ntt_fr * fq_peak / fr_peak          # per-proof algorithmic convention
     roofline = {"bound": "int32-modmul", "unit": "Fq-modmul/s", "peak": fq_peak,
                 "executed_modmul_per_proof": exec_fq, "executed_frac": exec_fq * batch / dt / fq_peak,
                 "achieved": algo_fq * batch / dt, "frac": algo_fq * batch / dt / fq_peak, "per_proof": per_proof,
                 "g1_accumulate_share_of_batch": acc_ms * 1e-3 / steps / dt,
-                "note": "executed = 10 Fq products per G1 bucket addition + 28 per G2 bucket addition (8 Fq2 products + 2 Fq2 squarings) "
-                        "+ NTT butterflies scaled by the Fr/Fq product cost; additions are counted on the device (non-zero digits), bucket "
+                "note": "executed = 10 Fq products per G1 XYZZ addition, 6.4 per G1 batched-affine addition, 28 / 17.6 for G2 (Fq2 product = 3 Fq "
+                        "products, square = 2) + NTT butterflies scaled by the Fr/Fq product cost; additions are counted on the device (non-zero digits), bucket "
                         "reductions, blinding multiplications and encodings are NOT counted (conservative).  frac uses SURVEY 8(d)'s fixed "
                         "176 n / 528 n convention, which over-counts the 0/1 witness scalars"}
     # two batches in flight: a second context (own streams and workspace, same resident CRS) driven by a second host thread, so
@@ -974,6 +995,8 @@ def main():
     ap.add_argument("--window-bits", dest="window_bits", type=int, default=0, help="0 = library default (20 bits from 2^20 terms, else <= 16)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-secondary", dest="secondary", action="store_false")
+    ap.add_argument("--affine-min-entries", dest="affine_min_entries", type=int, default=None, help="zk_ctx_set_opt(ZK_OPT_AFFINE_MIN_ENTRIES) on the bench contexts")
+    ap.add_argument("--affine-levels", dest="affine_levels", type=int, default=-1)
     ap.add_argument("--strong-log-n", dest="strong_log_n", type=int, default=24,
                     help="total terms (log2) of the fixed-total sharded MSM of secondary.msm_strong_scaling (BASELINE config 5); 0 = skip")
     args = ap.parse_args()

@@ -57,9 +57,10 @@ void zk_ctx_destroy(zk_ctx *ctx);
 int zk_ctx_sync(zk_ctx *ctx);
 /* Tuning options of a context (and of the prover lanes it owns).  Results never depend on them.
  *   ZK_OPT_AFFINE_MIN_ENTRIES  MSMs with at least this many (term, window) entries reduce their buckets with batched-affine
- *                              rounds (6 field products per addition instead of 10, one shared inversion per round, ~0.15 ms of
- *                              latency each) before the XYZZ pass.  Default -1 = never: on B200 the rounds measured no faster
- *                              than the XYZZ pass alone (profiles/r02_experiments.md); 0 = always.
+ *                              rounds (6.4 field products per addition instead of 10, one shared inversion per round, ~0.2 ms of
+ *                              latency each) before the XYZZ pass: +8 % MSM throughput with two MSMs in flight, +13 % for a
+ *                              256-proof batch, -3 % on one blocking 2^20 MSM (profiles/r02_experiments.md).  Default 2^22;
+ *                              -1 = never, 0 = always.
  *   ZK_OPT_AFFINE_LEVELS       number of rounds; -1 (default) = from the average bucket length.
  *   ZK_OPT_VERIFY_LANES        1 (default): the verifier's Miller loops and final exponentiations spread every Fq12 value over six
  *                              lanes of a warp; 0: one thread per proof (the round-1 kernels, kept as the A/B reference). */
@@ -202,10 +203,11 @@ int zk_bench_modmul(zk_ctx *ctx, int field, int blocks, int threads, int iters, 
  * count (bench.py's roofline block).  Disabled by default (no events are created). */
 int zk_ctx_profile(zk_ctx *ctx, int enable);
 int zk_ctx_profile_read(zk_ctx *ctx, double *total_ms, uint64_t *launches);
-/* Work executed by the MSMs of this context (and of its prover lanes) since the last zk_ctx_profile call: the number of bucket
- * additions (= non-zero signed digits) in G1 and in G2, counted on the device.  bench.py turns them into executed
- * Fq-modmul-equivalents for the proofs/sec roofline (one mixed addition = 10 products in the base field). */
-int zk_ctx_profile_counts(zk_ctx *ctx, uint64_t *g1_additions, uint64_t *g2_additions);
+/* Work executed by the MSMs of this context (and of its prover lanes) since the last zk_ctx_profile call, counted on the device:
+ * the number of bucket additions (= non-zero signed digits) in G1 and in G2, and how many of them were left to the XYZZ pass
+ * (the others were done by batched-affine rounds).  bench.py turns them into executed Fq-modmul-equivalents for the rooflines:
+ * an XYZZ mixed addition = 10 products in the base field, a batched-affine addition = 6.4. */
+int zk_ctx_profile_counts(zk_ctx *ctx, uint64_t *g1_additions, uint64_t *g2_additions, uint64_t *g1_xyzz, uint64_t *g2_xyzz);
 
 /* ---- Groth16 verification (the step after the proving path) ----------------------------------
  * zk_pvk: bellman_verifier::PreparedVerifyingKey<Bls12> resident on the device — e(alpha_g1, beta_g2), the Miller-loop

@@ -56,7 +56,7 @@ def test_hot_kernel_sass_uses_fused_wide_multiplies():
     assert "sm_100a" in listing
     names = subprocess.check_output("cuobjdump -sass %s | grep 'Function :'" % _lib.SO_PATH, shell=True).decode()
     # the two kernels that carry the G1 bucket additions: the XYZZ pass and the batched-affine backward pass (first round)
-    for key in ("k_accumulateI2FpI8FqParamsELi3", "k_ba_backwardI2FpI8FqParamsELb1ELi3"):
+    for key in ("k_accumulateI2FpI8FqParamsELi3", "k_ba_backwardI2FpI8FqParamsELb1ELi4"):
         fn = [l.split(":")[1].strip() for l in names.splitlines() if key in l]
         assert len(fn) == 1, (key, names)
         sass = subprocess.check_output(["cuobjdump", "-sass", "-fun", fn[0], _lib.SO_PATH], stderr=subprocess.STDOUT).decode()

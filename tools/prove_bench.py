@@ -28,6 +28,8 @@ if mode == "cpu":
 else:
     from zero_chain_b200 import groth16 as zk
     ctx = zk.Context(0)
+    if len(sys.argv) > 4:                       # batched-affine bucket rounds: min entries, levels
+        ctx.set_opt(zk.Context.OPT_AFFINE_MIN_ENTRIES, int(sys.argv[3])); ctx.set_opt(zk.Context.OPT_AFFINE_LEVELS, int(sys.argv[4]))
     g1 = lambda s: zk.scalar_mul_many(ctx, 1, zk.G1_GENERATOR, s)
     g2 = lambda s: zk.scalar_mul_many(ctx, 2, zk.G2_GENERATOR, s)
     t = time.time(); crs = sy.make_toy_crs(r1cs, g1, g2, seed=2); print("crs (gpu points) %.1fs" % (time.time() - t), flush=True)

@@ -58,7 +58,7 @@ SIGNATURES = {
     "zk_bench_modmul": (i32, [vp, i32, i32, i32, i32, C.POINTER(dbl), C.POINTER(dbl)]),
     "zk_ctx_profile": (i32, [vp, i32]),
     "zk_ctx_profile_read": (i32, [vp, C.POINTER(dbl), C.POINTER(C.c_uint64)]),
-    "zk_ctx_profile_counts": (i32, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "zk_ctx_profile_counts": (i32, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "zk_pvk_load": (i32, [vp, vp, sz, PP]),
     "zk_pvk_prepare": (i32, [vp, vp, sz, PP]),
     "zk_pvk_size": (sz, [vp]),

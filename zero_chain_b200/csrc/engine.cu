@@ -35,8 +35,8 @@ extern "C" int zk_ctx_create(int device, void *stream, zk_ctx **out) {
     cudaDeviceProp prop;
     ZK_CUDA(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
-    ZK_CUDA(cudaMalloc(&c->d_err, 16 * sizeof(int)));
-    ZK_CUDA(cudaMemsetAsync(c->d_err, 0, 16 * sizeof(int), c->stream));
+    ZK_CUDA(cudaMalloc(&c->d_err, 32 * sizeof(int)));       // [0..1] error flags, [8..9] task length / heavy-bucket count, [10..17] work counters
+    ZK_CUDA(cudaMemsetAsync(c->d_err, 0, 32 * sizeof(int), c->stream));
     c->h_pinned_cap = 1 << 20;
     ZK_CUDA(cudaMallocHost(&c->h_pinned, c->h_pinned_cap));
     *out = c;
@@ -395,20 +395,20 @@ extern "C" int zk_ctx_profile(zk_ctx *ctx, int enable) {
     ctx->prof_events.clear();
     ctx->prof_on = enable != 0;
     for (zk_ctx *c : {ctx, ctx->aux, ctx->aux2})             // work counters of this context and its lanes restart with the profile
-        if (c) { ZK_CUDA(cudaStreamSynchronize(c->stream)); ZK_CUDA(cudaMemsetAsync(c->d_err + 10, 0, 4 * sizeof(int), c->stream)); ZK_CUDA(cudaStreamSynchronize(c->stream)); }
+        if (c) { ZK_CUDA(cudaStreamSynchronize(c->stream)); ZK_CUDA(cudaMemsetAsync(c->d_err + 10, 0, 8 * sizeof(int), c->stream)); ZK_CUDA(cudaStreamSynchronize(c->stream)); }
     return ZK_OK;
 }
-extern "C" int zk_ctx_profile_counts(zk_ctx *ctx, uint64_t *g1_additions, uint64_t *g2_additions) {
-    if (!ctx || !g1_additions || !g2_additions) { zk_set_error("zk_ctx_profile_counts: NULL argument"); return ZK_ERR_INVALID; }
+extern "C" int zk_ctx_profile_counts(zk_ctx *ctx, uint64_t *g1_additions, uint64_t *g2_additions, uint64_t *g1_xyzz, uint64_t *g2_xyzz) {
+    if (!ctx || !g1_additions || !g2_additions || !g1_xyzz || !g2_xyzz) { zk_set_error("zk_ctx_profile_counts: NULL argument"); return ZK_ERR_INVALID; }
     ZK_TRY(zk_use_device(ctx));
-    *g1_additions = 0; *g2_additions = 0;
+    *g1_additions = 0; *g2_additions = 0; *g1_xyzz = 0; *g2_xyzz = 0;
     for (zk_ctx *c : {ctx, ctx->aux, ctx->aux2}) {
         if (!c) continue;
-        unsigned long long v[2] = {0, 0};
+        unsigned long long v[4] = {0, 0, 0, 0};
         ZK_CUDA(cudaStreamSynchronize(c->stream));
         if (c->tail) ZK_CUDA(cudaStreamSynchronize(c->tail));
         ZK_CUDA(cudaMemcpy(v, c->d_err + 10, sizeof(v), cudaMemcpyDeviceToHost));
-        *g1_additions += v[0]; *g2_additions += v[1];
+        *g1_additions += v[0]; *g2_additions += v[1]; *g1_xyzz += v[2]; *g2_xyzz += v[3];     // ints 10-11, 12-13, 14-15, 16-17 of d_err
     }
     return ZK_OK;
 }

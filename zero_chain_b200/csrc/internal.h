@@ -43,7 +43,7 @@ struct NttSlot { unsigned log_n = 0; bool valid = false; uint64_t last_use = 0; 
 
 // tuning options of a context (zk_ctx_set_opt); the prover lanes inherit them
 struct zk_opts {
-    long ba_min_entries = -1;          // ZK_OPT_AFFINE_MIN_ENTRIES; -1 = batched-affine rounds off (the measured default, profiles/r02_experiments.md)
+    long ba_min_entries = 1l << 22;    // ZK_OPT_AFFINE_MIN_ENTRIES; -1 = batched-affine rounds off
     long ba_levels = -1;               // ZK_OPT_AFFINE_LEVELS (-1 = from the average bucket length)
     long verify_lanes = 1;             // ZK_OPT_VERIFY_LANES: 1 = lane-parallel Miller loop / final exponentiation, 0 = thread per proof
 };

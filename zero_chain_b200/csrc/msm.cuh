@@ -195,10 +195,11 @@ __device__ __forceinline__ uint32_t scan_load(const uint32_t *in, size_t i, uint
 // accumulation kernel runs in waves of `capacity` (= resident threads) tasks; the length is chosen so that the
 // task count is just under a whole number of waves (a trailing partial wave costs a full wave's latency).
 static __global__ void k_pick_task_len(const uint32_t *__restrict__ total_entries, const uint32_t *__restrict__ sorted_entries, uint32_t *__restrict__ task_len,
-                                       uint32_t capacity, unsigned long long *__restrict__ work_counter) {
+                                       uint32_t capacity, unsigned long long *__restrict__ work_counter, unsigned long long *__restrict__ xyzz_counter) {
     task_len[1] = 0;                                           // heavy-bucket counter of k_combine_serial (next word)
     uint32_t total = *total_entries;                           // entries the XYZZ pass sees (after the batched-affine rounds)
-    *work_counter += *sorted_entries;                                    // executed bucket additions (non-zero digits) of this context, read by zk_ctx_profile_counts
+    *work_counter += *sorted_entries;                          // all bucket additions of this MSM (non-zero digits)
+    *xyzz_counter += total;                                    // ... of which this many are left to the XYZZ pass                                    // executed bucket additions (non-zero digits) of this context, read by zk_ctx_profile_counts
     uint32_t waves = (total + (uint32_t)TASK_LEN_MAX * capacity - 1) / ((uint32_t)TASK_LEN_MAX * capacity);
     if (waves < 2) waves = 2;                                   // small inputs: at least two waves of short tasks
     uint32_t target = (uint32_t)(0.97f * (float)waves * (float)capacity);

@@ -8,13 +8,12 @@
 // product-equivalents per addition.  Here ONE inversion serves a whole ROUND, and a round is three kernels:
 //
 //   k_ba_forward   thread: K consecutive output slots; classifies each pair, multiplies the denominators into a running
-//                  product, parks the exclusive prefix products (k-major, coalesced) and the pair sources; block: product
-//                  tree over its 128 thread totals -> one block total
-//   k_ba_invert    ONE block over the block totals: serial chunks + a product tree, a single field inversion (binary
+//                  product, parks the exclusive prefix products (k-major, coalesced) and the pair sources; warp: two shuffle
+//                  scans give every thread the product of the OTHER 31 thread totals, and the warp its total
+//   k_ba_invert    ONE block over the warp totals: serial chunks + a product tree, a single field inversion (binary
 //                  extended Euclid on one thread, ~90 us — the only serial step of the round), and the way back down
-//   k_ba_backward  block: rebuilds its product tree, walks it down from the inverted block total to the inverse of every
-//                  thread total; thread: peels the inverse of each denominator (2 products), finishes the affine addition
-//                  (3 products) and stores the sum
+//   k_ba_backward  thread: 1 / (own total) = 1 / (warp total) x (product of the others); peels the inverse of each
+//                  denominator (2 products), finishes the affine addition (3 products) and stores the sum
 //
 // A round halves every bucket: bucket b with m points yields ceil(m/2) points (an odd leftover is copied), so the outputs
 // are again grouped by bucket and the offsets come from one scan.  After `levels` rounds the (short) remainders go through
@@ -31,8 +30,8 @@
 namespace zkmsm {
 
 constexpr int BA_T = 128;                     // threads per block of the forward / backward kernels
-constexpr int BA_K_MIN = 8, BA_K_MAX = 32;    // additions per thread and round (chosen per round by the driver)
-constexpr int BA_MINB = 3;                    // resident blocks per SM of the backward kernel (168 registers)
+constexpr int BA_K = 32;                      // additions per thread and round (measured: 32 beats 16 / adaptive once the block trees are gone)
+constexpr int BA_MINB = 4;                    // resident blocks per SM of the backward kernel (128 registers; measured 1-3 % faster than 3)
 constexpr int BA_MAX_LEVELS = 8;
 constexpr int BA_INV_T = 512;                 // threads of the single inversion block
 constexpr uint32_t BA_NONE = 0xffffffffu;     // "no second point": the odd leftover of a bucket
@@ -74,27 +73,48 @@ __device__ __forceinline__ Affine<F> ba_load_point(const Affine<F> *pts, uint32_
     return p;
 }
 
-// ---- block-level product tree over BA_T thread totals (heap layout: node 1 = root, leaves BA_T .. 2 BA_T - 1) ----
+// ---- warp-level products of the thread totals (no block barriers: the warps of a block stay independent) ----
 template <class F>
-__device__ __forceinline__ void ba_tree_up(F *node, int t) {
-    for (int s = BA_T / 2; s >= 1; s >>= 1) {
-        __syncthreads();
-        if (t < s) node[s + t] = node[2 * (s + t)] * node[2 * (s + t) + 1];
-    }
-    __syncthreads();
+__device__ __forceinline__ F ba_shfl(const F &v, int delta, bool up) {
+    F r;
+    const uint32_t *s = reinterpret_cast<const uint32_t *>(&v);
+    uint32_t *d = reinterpret_cast<uint32_t *>(&r);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(F) / 4); k++) d[k] = up ? __shfl_up_sync(0xffffffffu, s[k], delta) : __shfl_down_sync(0xffffffffu, s[k], delta);
+    return r;
 }
-// node[1] must hold the INVERSE of the root product; afterwards leaf BA_T + t holds the inverse of thread t's total
 template <class F>
-__device__ __forceinline__ void ba_tree_down(F *node, int t) {
-    for (int s = 1; s < BA_T; s <<= 1) {
-        __syncthreads();
-        if (t < s) {
-            F inv = node[s + t], l = node[2 * (s + t)], r = node[2 * (s + t) + 1];
-            node[2 * (s + t)] = inv * r;
-            node[2 * (s + t) + 1] = inv * l;
-        }
+__device__ __forceinline__ F ba_sel(bool c, const F &a, const F &b) {
+    F r;
+    const uint32_t *pa = reinterpret_cast<const uint32_t *>(&a), *pb = reinterpret_cast<const uint32_t *>(&b);
+    uint32_t *d = reinterpret_cast<uint32_t *>(&r);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(F) / 4); k++) d[k] = c ? pa[k] : pb[k];
+    return r;
+}
+// For the 32 thread totals T_0 .. T_31 of a warp: `others` = product of all T_j, j != lane (prefix x suffix, two Kogge-Stone scans
+// of 5 steps each), `all` = the warp's total in every lane.  1 / T_lane = (1 / all) * others.
+template <class F>
+__device__ __forceinline__ void ba_warp_products(const F &t, F &others, F &all) {
+    const int lane = threadIdx.x & 31;
+    F inc = t, dec = t;
+#pragma unroll 1
+    for (int d = 1; d < 32; d <<= 1) {
+        F y = ba_shfl(inc, d, true), p = inc * y;
+        inc = ba_sel(lane >= d, p, inc);
+        F z = ba_shfl(dec, d, false), q = dec * z;
+        dec = ba_sel(lane + d < 32, q, dec);
     }
-    __syncthreads();
+    F pre = ba_shfl(inc, 1, true), suf = ba_shfl(dec, 1, false);
+    pre = ba_sel(lane == 0, F::one(), pre);
+    suf = ba_sel(lane == 31, F::one(), suf);
+    others = pre * suf;
+    F tot;
+    const uint32_t *s = reinterpret_cast<const uint32_t *>(&inc);
+    uint32_t *dd = reinterpret_cast<uint32_t *>(&tot);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(F) / 4); k++) dd[k] = __shfl_sync(0xffffffffu, s[k], 31);
+    all = tot;
 }
 
 // ---- forward ------------------------------------------------------------------------------------------------------
@@ -115,8 +135,6 @@ template <class F, bool FIRST>
 __global__ void __launch_bounds__(BA_T, 4) k_ba_forward(const Affine<F> *__restrict__ in_pts, const uint32_t *__restrict__ sorted,
                                                          const uint32_t *__restrict__ off_in, const uint32_t *__restrict__ off_out, uint32_t n_buckets, int K,
                                                          F *__restrict__ prefix, uint2 *__restrict__ srcs, F *__restrict__ block_totals) {
-    extern __shared__ unsigned char ba_smem[];
-    F *node = reinterpret_cast<F *>(ba_smem);
     const uint32_t total = off_out[n_buckets];
     const uint32_t n_blocks = (total + BA_T * K - 1) / (BA_T * K);
     if (blockIdx.x >= n_blocks) return;                    // the grid is sized for the host-side upper bound of `total`
@@ -164,10 +182,11 @@ __global__ void __launch_bounds__(BA_T, 4) k_ba_forward(const Affine<F> *__restr
             run = run * den;
         }
     }
-    ba_store_f(prefix + (size_t)K * T_total + tid, run);      // thread total (1 for idle threads)
-    node[BA_T + t] = run;
-    ba_tree_up(node, t);
-    if (t == 0) ba_store_f(block_totals + blockIdx.x, node[1]);
+    // the product of the OTHER 31 thread totals of this warp goes to plane K; the warp's total to the round's inversion
+    F others, all;
+    ba_warp_products(run, others, all);
+    ba_store_f(prefix + (size_t)K * T_total + tid, others);
+    if ((t & 31) == 0) ba_store_f(block_totals + (tid >> 5), all);
 }
 
 // ---- the round's single inversion ----------------------------------------------------------------------------------
@@ -178,7 +197,7 @@ __global__ void __launch_bounds__(BA_INV_T) k_ba_invert(const F *__restrict__ to
     extern __shared__ unsigned char ba_smem[];
     F *node = reinterpret_cast<F *>(ba_smem);                // heap of 2 * BA_INV_T nodes
     const uint32_t total = off_out[n_buckets];
-    const uint32_t n = (total + BA_T * K - 1) / (BA_T * K);
+    const uint32_t n = ((total + BA_T * K - 1) / (BA_T * K)) * (BA_T / 32);       // one total per warp of the live blocks
     const int t = threadIdx.x;
     const uint32_t per = (n + BA_INV_T - 1) / BA_INV_T, c0 = t * per, c1 = c0 + per < n ? c0 + per : n;
     F run = F::one();
@@ -214,31 +233,16 @@ __global__ void __launch_bounds__(BA_T, MINB) k_ba_backward(const Affine<F> *__r
                                                              Affine<F> *__restrict__ out_pts) {
     constexpr int PV = (int)(sizeof(Affine<F>) / 16), FV = (int)(sizeof(F) / 16), SLOT = 2 * PV + FV;     // two points + one prefix element
     extern __shared__ unsigned char ba_smem[];
-    F *node = reinterpret_cast<F *>(ba_smem);
-    uint4 *stage = reinterpret_cast<uint4 *>(ba_smem + 2 * BA_T * sizeof(F));
-#ifdef ZK_EXPERIMENTS
-    const bool notree = K < 0;
-    if (notree) K = -K;
-#endif
+    uint4 *stage = reinterpret_cast<uint4 *>(ba_smem);
     const uint32_t total = off_out[n_buckets];
     const uint32_t n_blocks = (total + BA_T * K - 1) / (BA_T * K);
     if (blockIdx.x >= n_blocks) return;
     const int t = threadIdx.x;
     const size_t T_total = (size_t)gridDim.x * BA_T, tid = (size_t)blockIdx.x * BA_T + t;
     const uint32_t o0 = (uint32_t)tid * K;
-    // inverse of this thread's total: rebuild the block's product tree, plant the inverted block total at the root, walk down
-#ifdef ZK_EXPERIMENTS
-    if (notree) node[BA_T + t] = ba_load_f(block_inv + blockIdx.x);      // timing experiment only (wrong results): no product tree in this kernel
-    else
-#endif
-    {
-    node[BA_T + t] = ba_load_f(prefix + (size_t)K * T_total + tid);
-    ba_tree_up(node, t);
-    if (t == 0) node[1] = ba_load_f(block_inv + blockIdx.x);
-    ba_tree_down(node, t);
-    }
     if (o0 >= total) return;
-    F inv = node[BA_T + t];
+    // inverse of this thread's total = (inverse of the warp's total) x (product of the other 31 totals of the warp)
+    F inv = ba_load_f(block_inv + (tid >> 5)) * ba_load_f(prefix + (size_t)K * T_total + tid);
     const uint32_t o1 = o0 + K < total ? o0 + K : total;
     // software pipeline: while addition o is finished, the operands of o - 1 (two points, one prefix product) stream into
     // this thread's shared-memory slot with cp.async — the gather latency hides behind five Montgomery products
@@ -289,8 +293,8 @@ __global__ void __launch_bounds__(BA_T, MINB) k_ba_backward(const Affine<F> *__r
 }
 
 // dynamic shared memory of the three kernels
-template <class F> constexpr size_t ba_smem_forward() { return 2 * BA_T * sizeof(F); }
-template <class F> constexpr size_t ba_smem_backward() { return 2 * BA_T * sizeof(F) + (size_t)BA_T * (2 * sizeof(Affine<F>) + sizeof(F)); }
+template <class F> constexpr size_t ba_smem_forward() { return 0; }
+template <class F> constexpr size_t ba_smem_backward() { return (size_t)BA_T * (2 * sizeof(Affine<F>) + sizeof(F)); }
 template <class F> constexpr size_t ba_smem_invert() { return 2 * BA_INV_T * sizeof(F); }
 
 }  // namespace zkmsm

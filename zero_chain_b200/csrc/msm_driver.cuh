@@ -85,10 +85,12 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
         k_fine_sort<<<dim3(512, (unsigned)n_dom), 1024, 0, st>>>(ctx->sorted2.as<uint32_t>(), ctx->coarse_off.as<uint32_t>(), digits, e_dom, 512, low,
                                                                  ctx->sizes.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(), ctx->sorted.as<uint32_t>());
     }
-    // 2b. batched-affine rounds (msm_batchaff.cuh): each round halves every bucket at ~6.3 products per addition instead of the 10
-    //     of an XYZZ mixed addition, with ONE shared field inversion per round.  The number of rounds follows the average bucket
-    //     length (the host only knows the upper bound E / NB; sparse scalars make the rounds cheaper, not wrong): the XYZZ pass
-    //     that follows wants ~3 points per bucket left.
+    // 2b. batched-affine rounds (msm_batchaff.cuh): each round halves every bucket at ~6.4 products per addition instead of the 10
+    //     of an XYZZ mixed addition, with ONE shared field inversion per round.  Measured (2^20 terms, 26 entries per bucket): two
+    //     rounds give +8 % MSM throughput with two MSMs in flight and -3 % on a blocking call; a 256-proof batch gains 13 %.  A
+    //     round costs ~0.2 ms of latency (its inversion), so only MSMs with >= 2^22 entries take them (zk_ctx_set_opt), and the
+    //     number of rounds follows the average bucket length (the host knows the upper bound E / NB; sparse scalars make the
+    //     rounds cheaper, not wrong).
     const Affine<F> *cur_pts = (const Affine<F> *)b->d_tbl;
     const uint32_t *cur_sorted = ctx->sorted.as<uint32_t>(), *cur_off = ctx->bucket_off.as<uint32_t>(), *cur_sizes = ctx->sizes.as<uint32_t>();
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;      // zk_ctx_profile: the bucket-accumulation stage (affine rounds, if any, + the XYZZ pass)
@@ -96,7 +98,7 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
         int levels = 0;
         if (ctx->opts.ba_min_entries >= 0 && (long)E >= ctx->opts.ba_min_entries) {      // a round costs ~0.1 ms of latency (its inversion): small MSMs stay on the XYZZ pass alone
             if (ctx->opts.ba_levels >= 0) levels = (int)(ctx->opts.ba_levels < BA_MAX_LEVELS ? ctx->opts.ba_levels : BA_MAX_LEVELS);
-            else for (size_t avg = E / NB; avg >= 6 && levels < BA_MAX_LEVELS; avg >>= 1) levels++;
+            else for (size_t avg = E / NB; avg >= 12 && levels < BA_MAX_LEVELS; avg >>= 1) levels++;      // 26 per bucket -> 2 rounds, 76 -> 3 (measured)
         }
         if (ctx->prof_on && levels > 0) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, st); }
         size_t in_max = E;
@@ -112,8 +114,8 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
                 ZK_CUDA(cudaFuncSetAttribute(k_ba_backward<F, true, BA_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba_smem_backward<F>()));
                 ZK_CUDA(cudaFuncSetAttribute(k_ba_backward<F, false, BA_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba_smem_backward<F>()));
 #ifdef ZK_EXPERIMENTS
-                ZK_CUDA(cudaFuncSetAttribute(k_ba_backward<F, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba_smem_backward<F>()));
-                ZK_CUDA(cudaFuncSetAttribute(k_ba_backward<F, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba_smem_backward<F>()));
+                ZK_CUDA(cudaFuncSetAttribute(k_ba_backward<F, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba_smem_backward<F>()));
+                ZK_CUDA(cudaFuncSetAttribute(k_ba_backward<F, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba_smem_backward<F>()));
 #endif
             }
             if (ba_smem_invert<F>() > 48 * 1024)
@@ -121,9 +123,7 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
         }
         for (int l = 0; l < levels; l++) {
             const size_t out_max = (in_max + NB) / 2 + 1;
-            // additions per thread: as many as leave >= ~4 waves of blocks (the block-level product trees cost a fixed ~24 warp-products)
-            int K = (int)(out_max / ((size_t)BA_T * ctx->sm_count * BA_MINB * 4));
-            K = K < BA_K_MIN ? BA_K_MIN : (K > BA_K_MAX ? BA_K_MAX : K);
+            int K = BA_K;
             if (k_force > 0) K = k_force;
             const unsigned grid = (unsigned)((out_max + (size_t)BA_T * K - 1) / ((size_t)BA_T * K));
             const size_t T_total = (size_t)grid * BA_T;
@@ -132,8 +132,9 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
             ZK_TRY(off_o->reserve((NB + 1) * 4)); ZK_TRY(sz_o->reserve((NB + 1) * 4));
             ZK_TRY(ctx->aff_scratch.reserve((size_t)(K + 1) * T_total * sizeof(F)));
             ZK_TRY(ctx->aff_srcs.reserve(out_max * sizeof(uint2)));
-            ZK_TRY(ctx->aff_tot.reserve(3 * (size_t)grid * sizeof(F)));
-            F *tot = ctx->aff_tot.as<F>(), *tot_scr = tot + grid, *tot_inv = tot + 2 * (size_t)grid;
+            const size_t n_tot = (size_t)grid * (BA_T / 32);            // one total per warp
+            ZK_TRY(ctx->aff_tot.reserve(3 * n_tot * sizeof(F)));
+            F *tot = ctx->aff_tot.as<F>(), *tot_scr = tot + n_tot, *tot_inv = tot + 2 * n_tot;
             k_half_sizes<<<(unsigned)((NB + 255) / 256), 256, 0, st>>>(cur_off, sz_o->as<uint32_t>(), (uint32_t)NB);
             exclusive_scan<false>(sz_o->as<uint32_t>(), off_o->as<uint32_t>(), NB, ctx->scan_scratch.as<uint32_t>(), st);
             const uint32_t *off_out = off_o->as<uint32_t>();
@@ -144,14 +145,11 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
                 k_ba_forward<F, false><<<grid, BA_T, ba_smem_forward<F>(), st>>>(cur_pts, nullptr, cur_off, off_out, (uint32_t)NB, K, ctx->aff_scratch.as<F>(),
                                                                                 ctx->aff_srcs.as<uint2>(), tot);
             k_ba_invert<F><<<1, BA_INV_T, ba_smem_invert<F>(), st>>>(tot, off_out, (uint32_t)NB, K, tot_scr, tot_inv);
-            int Kb = K;
-#ifdef ZK_EXPERIMENTS
-            if (getenv("ZK_BA_NOTREE")) Kb = -K;
-#endif
+            const int Kb = K;
 #define ZK_BA_BWD(FIRST_, MB_) k_ba_backward<F, FIRST_, MB_><<<grid, BA_T, ba_smem_backward<F>(), st>>>(cur_pts, off_out, (uint32_t)NB, Kb, ctx->aff_scratch.as<F>(), \
                                                                                                     ctx->aff_srcs.as<uint2>(), tot_inv, pts_o->as<Affine<F>>())
 #ifdef ZK_EXPERIMENTS
-            if (minb == 4) { if (l == 0) ZK_BA_BWD(true, 4); else ZK_BA_BWD(false, 4); } else
+            if (minb == 3) { if (l == 0) ZK_BA_BWD(true, 3); else ZK_BA_BWD(false, 3); } else
 #endif
             { if (l == 0) ZK_BA_BWD(true, BA_MINB); else ZK_BA_BWD(false, BA_MINB); }
 #undef ZK_BA_BWD
@@ -163,7 +161,7 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
     uint32_t *d_task_len = (uint32_t *)(ctx->d_err + 8);
     const uint32_t capacity = (uint32_t)ctx->sm_count * 3u * 128u;      // k_accumulate: 3 CTAs of 128 threads per SM
     unsigned long long *d_work = (unsigned long long *)(ctx->d_err + (sizeof(F) == sizeof(Fq) ? 10 : 12));   // G1 / G2 addition counters
-    k_pick_task_len<<<1, 1, 0, st>>>(cur_off + NB, ctx->bucket_off.as<uint32_t>() + NB, d_task_len, capacity, d_work);
+    k_pick_task_len<<<1, 1, 0, st>>>(cur_off + NB, ctx->bucket_off.as<uint32_t>() + NB, d_task_len, capacity, d_work, d_work + 2);
     exclusive_scan<true>(cur_sizes, ctx->task_off.as<uint32_t>(), NB, ctx->scan_scratch.as<uint32_t>(), st, d_task_len);
     // 3. accumulate + combine.  The payload of an entry is its position in the domain = [w][i] index;
     //    with tables that is the table index when n == b->n (checked by the callers).

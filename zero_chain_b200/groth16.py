@@ -84,10 +84,11 @@ class Context:
         return ms.value, n.value
 
     def profile_counts(self):
-        """(G1 bucket additions, G2 bucket additions) executed by this context's MSMs (lanes included) since profile()."""
-        a, b = C.c_uint64(), C.c_uint64()
-        _ck(_lib.lib().zk_ctx_profile_counts(self._h, C.byref(a), C.byref(b)))
-        return a.value, b.value
+        """(G1 bucket additions, G2 bucket additions, G1 left to the XYZZ pass, G2 left to the XYZZ pass) executed by this
+        context's MSMs (lanes included) since profile()."""
+        v = [C.c_uint64() for _ in range(4)]
+        _ck(_lib.lib().zk_ctx_profile_counts(self._h, *[C.byref(x) for x in v]))
+        return tuple(x.value for x in v)
 
     def close(self):
         if self._h:
