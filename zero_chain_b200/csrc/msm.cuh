@@ -354,6 +354,9 @@ __global__ void __launch_bounds__(128) k_combine_warp(const XYZZ<F> *__restrict_
 //   stage 2: k_sum_points over the slice partials -> X[dom][bit]
 //   stage 3: k_finish_bits: thread per dom, R = X_0 + 2 (X_1 + 2 (X_2 + ...))
 constexpr int RED_T = 128, RED_SLICE = 512;
+#ifndef ZK_RC_MINB
+#define ZK_RC_MINB 2      // resident blocks per SM of the G1 row/column sums (register budget 255 / 168 / 128)
+#endif
 // warp-level tree over the 32 lane accumulators of one warp (slot = this warp's 32 shared-memory points)
 template <class F>
 __device__ __forceinline__ void warp_tree(XYZZ<F> *slot, XYZZ<F> &acc, uint32_t lane) {
@@ -438,7 +441,7 @@ __global__ void __launch_bounds__(RED_T) k_finish_bits(const XYZZ<F> *__restrict
 // pseudo-domains of NR points finishes both weighted sums.
 // GL lanes per item: 8 for many domains (work-bound), 32 inside a warp.
 template <class F, int GL>
-__global__ void __launch_bounds__(RED_T) k_rowcol_sums(const XYZZ<F> *__restrict__ B, int N, int s, int n_dom, XYZZ<F> *__restrict__ rc) {
+__global__ void __launch_bounds__(RED_T, (sizeof(F) == sizeof(Fq) ? ZK_RC_MINB : 1)) k_rowcol_sums(const XYZZ<F> *__restrict__ B, int N, int s, int n_dom, XYZZ<F> *__restrict__ rc) {
     extern __shared__ unsigned char smraw[];
     const uint32_t lane = threadIdx.x & 31, sub = lane & (GL - 1);
     XYZZ<F> *slot = reinterpret_cast<XYZZ<F> *>(smraw) + (threadIdx.x >> 5) * 32;
