@@ -354,6 +354,10 @@ __global__ void __launch_bounds__(128) k_combine_warp(const XYZZ<F> *__restrict_
 //   stage 2: k_sum_points over the slice partials -> X[dom][bit]
 //   stage 3: k_finish_bits: thread per dom, R = X_0 + 2 (X_1 + 2 (X_2 + ...))
 constexpr int RED_T = 128, RED_SLICE = 512;
+#ifndef ZK_RC_GL
+#define ZK_RC_GL 8        // lanes per row / column of the batched-domain bucket reduction
+#endif
+constexpr int RC_GL = ZK_RC_GL;
 #ifndef ZK_RC_MINB
 #define ZK_RC_MINB 2      // resident blocks per SM of the G1 row/column sums (register budget 255 / 168 / 128)
 #endif

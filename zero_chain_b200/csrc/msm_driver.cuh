@@ -226,12 +226,13 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
         Rdom = tables ? R : R + 1;
         XYZZ<F> *rc = ctx->red_rows.as<XYZZ<F>>(), *Rrc = R + n_dom + 2;
         if (sm_warp > 48 * 1024) {
-            ZK_CUDA(cudaFuncSetAttribute(k_rowcol_sums<F, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_warp));
+            ZK_CUDA(cudaFuncSetAttribute(k_rowcol_sums<F, RC_GL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_warp));
         }
         size_t n_items = n_dom * (size_t)(nr + nc);
         if (n_dom >= 8) {
             ZK_CUDA(cudaMemsetAsync(rc, 0, 2 * n_dom * (size_t)nr * pt, st));      // infinity padding of the column halves
-            k_rowcol_sums<F, 8><<<(unsigned)((((n_items + 3) / 4) * 32 + RED_T - 1) / RED_T), RED_T, sm_warp, st>>>(buckets, nbins, s, (int)n_dom, rc);
+            constexpr int per_warp = 32 / RC_GL;      // (domain, row / column) items per warp
+            k_rowcol_sums<F, RC_GL><<<(unsigned)((((n_items + per_warp - 1) / per_warp) * 32 + RED_T - 1) / RED_T), RED_T, sm_warp, st>>>(buckets, nbins, s, (int)n_dom, rc);
         } else {
             const size_t n_slots = 2 * n_dom * (size_t)nr;
             const int longest = (1 << s) > nr + 1 ? (1 << s) : nr + 1;
