@@ -142,7 +142,7 @@ int zk_params_write(zk_ctx *ctx, const zk_params *p, uint8_t *out);
 int zk_params_write_vk(zk_ctx *ctx, const zk_params *p, uint8_t *out);
 /* Parameters::read(buf, checked = true) with a decoded-CRS cache on disk (the "FIX: too heavy" read at
  * core/proofs/src/crypto_components.rs:320-328).  If `cache_path` holds the decoded Montgomery points of exactly these bytes
- * (SHA-256 of the whole stream, length and vector counts are compared), they are uploaded as they are — no decoding, no on-curve
+ * (SHA-256 of the whole stream, length and vector counts are compared, and the cached points carry their own SHA-256), they are uploaded as they are — no decoding, no on-curve
  * or subgroup tests (*cache_hit = 1).  Otherwise the stream goes through the full CHECKED load and the cache file is (re)written
  * atomically (*cache_hit = 0); a cache that cannot be written is not an error.  cache_hit may be NULL. */
 int zk_params_load_cached(zk_ctx *ctx, const uint8_t *pk_bytes, size_t len, const char *cache_path, int *cache_hit, zk_params **out);

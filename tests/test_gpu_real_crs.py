@@ -148,6 +148,13 @@ def test_decoded_crs_cache(ctx, pk, params, tmp_path):
     other = bytearray(pk); other[pr.params_layout(pk)["l"][0] + 95] ^= 1
     with pytest.raises(zk.SynthesisError):
         zk.Parameters.read_cached(ctx, bytes(other), path)
+    # a cache whose BODY was altered (header intact) must not be trusted: it is ignored and rewritten
+    with open(path, "r+b") as f:
+        f.seek(5_000_000); b = f.read(1); f.seek(5_000_000); f.write(bytes([b[0] ^ 1]))
+    p4 = zk.Parameters.read_cached(ctx, pk, path)
+    assert not p4.cache_hit and zk.create_proof(pa, p4, 11, 22) == want
+    p4.free()
+    assert zk.Parameters.read_cached(ctx, pk, path).cache_hit
     # a truncated cache file is ignored and rewritten
     open(path, "r+b").truncate(1 << 20)
     p3 = zk.Parameters.read_cached(ctx, pk, path)

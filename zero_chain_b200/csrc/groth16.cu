@@ -251,6 +251,7 @@ struct CacheHeader {
     uint8_t sha[32];
     uint64_t cnt[6];
     uint64_t g1_points, g2_points;
+    uint8_t body_sha[32];       // SHA-256 of the decoded points that follow: a hit skips every check, so the body must be what was written
 };
 }  // namespace
 extern "C" int zk_params_load_cached(zk_ctx *ctx, const uint8_t *buf, size_t len, const char *cache_path, int *cache_hit, zk_params **out) {
@@ -271,9 +272,10 @@ extern "C" int zk_params_load_cached(zk_ctx *ctx, const uint8_t *buf, size_t len
     if (FILE *f = fopen(cache_path, "rb")) {
         CacheHeader got;
         std::vector<uint8_t> body;
-        bool ok = fread(&got, sizeof(got), 1, f) == 1 && memcmp(&got, &want, sizeof(got)) == 0;
+        bool ok = fread(&got, sizeof(got), 1, f) == 1 && memcmp(&got, &want, offsetof(CacheHeader, body_sha)) == 0;
         if (ok) { body.resize(b1 + b2); ok = fread(body.data(), 1, b1 + b2, f) == b1 + b2 && fgetc(f) == EOF; }
         fclose(f);
+        if (ok) { uint8_t h[32]; Sha256 sh; sh.update(body.data(), body.size()); sh.finish(h); ok = memcmp(h, got.body_sha, 32) == 0; }
         if (ok) {
             ZK_TRY(ctx->stage_b.reserve(b1 + 8 * sizeof(G1Affine)));
             ZK_TRY(ctx->stage_c.reserve(b2 + 8 * sizeof(G2Affine)));
@@ -291,6 +293,7 @@ extern "C" int zk_params_load_cached(zk_ctx *ctx, const uint8_t *buf, size_t len
     ZK_CUDA(cudaMemcpyAsync(body.data() + b1, ctx->stage_c.p, b2, cudaMemcpyDeviceToHost, ctx->stream));
     ZK_CUDA(cudaStreamSynchronize(ctx->stream));
     ZK_TRY(params_from_device(ctx, L, ctx->stage_b.as<G1Affine>(), ctx->stage_c.as<G2Affine>(), out));
+    { Sha256 sh; sh.update(body.data(), body.size()); sh.finish(want.body_sha); }
     std::string tmp = std::string(cache_path) + ".tmp";
     if (FILE *f = fopen(tmp.c_str(), "wb")) {           // a cache that cannot be written is not an error of the load
         bool ok = fwrite(&want, sizeof(want), 1, f) == 1 && fwrite(body.data(), 1, body.size(), f) == body.size();
