@@ -46,6 +46,7 @@ extern "C" void zk_ctx_destroy(zk_ctx *c) {
     if (!c) return;
     if (c->aux) { zk_ctx_destroy(c->aux); c->aux = nullptr; }
     if (c->aux2) { zk_ctx_destroy(c->aux2); c->aux2 = nullptr; }
+    if (c->aux3) { zk_ctx_destroy(c->aux3); c->aux3 = nullptr; }
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = {&c->scalars, &c->digits, &c->tile_hist, &c->tile_off, &c->sizes, &c->bucket_off, &c->task_off, &c->scan_scratch,
@@ -63,7 +64,7 @@ extern "C" void zk_ctx_destroy(zk_ctx *c) {
 }
 extern "C" int zk_ctx_set_opt(zk_ctx *c, int opt, long value) {
     if (!c) { zk_set_error("zk_ctx_set_opt: NULL ctx"); return ZK_ERR_INVALID; }
-    for (zk_ctx *x : {c, c->aux, c->aux2}) {
+    for (zk_ctx *x : {c, c->aux, c->aux2, c->aux3}) {
         if (!x) continue;
         if (opt == ZK_OPT_AFFINE_MIN_ENTRIES) x->opts.ba_min_entries = value;
         else if (opt == ZK_OPT_AFFINE_LEVELS) x->opts.ba_levels = value;
@@ -394,7 +395,7 @@ extern "C" int zk_ctx_profile(zk_ctx *ctx, int enable) {
     for (cudaEvent_t ev : ctx->prof_events) cudaEventDestroy(ev);
     ctx->prof_events.clear();
     ctx->prof_on = enable != 0;
-    for (zk_ctx *c : {ctx, ctx->aux, ctx->aux2})             // work counters of this context and its lanes restart with the profile
+    for (zk_ctx *c : {ctx, ctx->aux, ctx->aux2, ctx->aux3})  // work counters of this context and its lanes restart with the profile
         if (c) { ZK_CUDA(cudaStreamSynchronize(c->stream)); ZK_CUDA(cudaMemsetAsync(c->d_err + 10, 0, 8 * sizeof(int), c->stream)); ZK_CUDA(cudaStreamSynchronize(c->stream)); }
     return ZK_OK;
 }
@@ -402,7 +403,7 @@ extern "C" int zk_ctx_profile_counts(zk_ctx *ctx, uint64_t *g1_additions, uint64
     if (!ctx || !g1_additions || !g2_additions || !g1_xyzz || !g2_xyzz) { zk_set_error("zk_ctx_profile_counts: NULL argument"); return ZK_ERR_INVALID; }
     ZK_TRY(zk_use_device(ctx));
     *g1_additions = 0; *g2_additions = 0; *g1_xyzz = 0; *g2_xyzz = 0;
-    for (zk_ctx *c : {ctx, ctx->aux, ctx->aux2}) {
+    for (zk_ctx *c : {ctx, ctx->aux, ctx->aux2, ctx->aux3}) {
         if (!c) continue;
         unsigned long long v[4] = {0, 0, 0, 0};
         ZK_CUDA(cudaStreamSynchronize(c->stream));

@@ -331,10 +331,10 @@ __global__ void k_put_terms(const uint4 *__restrict__ terms, int sel0, int sel1,
 // block then sums the selected powers: 4 per thread, then a 6-level tree — about 2.5x less latency for the same group element.
 constexpr int SCALE_T = 64;
 __global__ void __launch_bounds__(SCALE_T) k_scale_points(const G1XYZZ *__restrict__ ga, const G1XYZZ *__restrict__ gb1, const uint32_t *__restrict__ terms,
-                                                          size_t batch, G1XYZZ *__restrict__ T) {
+                                                          size_t batch, int j, G1XYZZ *__restrict__ T) {
     __shared__ G1XYZZ pw[255];                                                   // 2^i P, i <= 254; reused for the tree (47.8 KB)
-    const size_t id = blockIdx.x;
-    const size_t b = id >> 1; const int j = (int)(id & 1), t = threadIdx.x;
+    const size_t b = blockIdx.x, id = 2 * b + j;                                 // one launch per product kind j (each on the lane that made its point)
+    const int t = threadIdx.x;
     const uint32_t *k = terms + (b * 4 + (j ? 1 : 2)) * 8;                       // j=0: s, j=1: r
     int top = -1;
     for (int i = 7; i >= 0 && top < 0; i--) if (k[i]) top = 32 * i + 31 - __clz(k[i]);
@@ -358,17 +358,22 @@ __global__ void __launch_bounds__(SCALE_T) k_scale_points(const G1XYZZ *__restri
     }
     if (t == 0) T[id] = part[0];
 }
-// thread per proof: g_c = T0 + T1 + H' + L; write Proof (compressed a | b | c)
-__global__ void __launch_bounds__(64) k_finish_proofs(const G1XYZZ *__restrict__ ga, const G2XYZZ *__restrict__ gb, const G1XYZZ *__restrict__ T,
+// block of three warps per 32 proofs, one warp per proof element, so that the three affine conversions (a field inversion each) of a
+// proof run side by side: warp 0 encodes A, warp 1 B (G2), warp 2 forms g_c = T0 + T1 + H' + L and encodes it.  Proof::write layout:
+// compressed a | b | c.
+__global__ void __launch_bounds__(96) k_finish_proofs(const G1XYZZ *__restrict__ ga, const G2XYZZ *__restrict__ gb, const G1XYZZ *__restrict__ T,
                                                       const G1XYZZ *__restrict__ H, const G1XYZZ *__restrict__ L, size_t batch, uint8_t *__restrict__ out) {
-    size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t b = (size_t)blockIdx.x * 32 + (threadIdx.x & 31);
+    const int which = threadIdx.x >> 5;
     if (b >= batch) return;
-    G1XYZZ c = T[2 * b];
-    c.add(T[2 * b + 1]); c.add(H[b]); c.add(L[b]);
     uint8_t *o = out + b * 192;
-    zkcodec::encode_point(o, ga[b].to_affine(), true);
-    zkcodec::encode_point(o + 48, gb[b].to_affine(), true);
-    zkcodec::encode_point(o + 144, c.to_affine(), true);
+    if (which == 0) zkcodec::encode_point(o, ga[b].to_affine(), true);
+    else if (which == 1) zkcodec::encode_point(o + 48, gb[b].to_affine(), true);
+    else {
+        G1XYZZ c = T[2 * b];
+        c.add(T[2 * b + 1]); c.add(H[b]); c.add(L[b]);
+        zkcodec::encode_point(o + 144, c.to_affine(), true);
+    }
 }
 }  // namespace
 
@@ -377,21 +382,20 @@ __global__ void __launch_bounds__(64) k_finish_proofs(const G1XYZZ *__restrict__
 // keeping the error text of the failure that caused the exit.
 namespace {
 struct LaneEvents {
-    cudaEvent_t b = nullptr, g2 = nullptr, a = nullptr, l3 = nullptr;
-    zk_ctx *lane2 = nullptr, *lane3 = nullptr;
+    cudaEvent_t b = nullptr, g2 = nullptr, a = nullptr, l3 = nullptr, l4 = nullptr;
+    zk_ctx *lane2 = nullptr, *lane3 = nullptr, *lane4 = nullptr;
     bool lanes_started = false, completed = false;
     int create() {
-        for (cudaEvent_t *e : {&b, &g2, &a, &l3}) ZK_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        for (cudaEvent_t *e : {&b, &g2, &a, &l3, &l4}) ZK_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         return ZK_OK;
     }
     ~LaneEvents() {
         if (lanes_started && !completed) {
             std::string keep = zk_last_error();
-            cudaStreamSynchronize(lane2->stream); cudaStreamSynchronize(lane3->stream);
-            zk_check_err_flag(lane2); zk_check_err_flag(lane3);
+            for (zk_ctx *l : {lane2, lane3, lane4}) { cudaStreamSynchronize(l->stream); zk_check_err_flag(l); }
             zk_set_error("%s", keep.c_str());
         }
-        for (cudaEvent_t e : {b, g2, a, l3}) if (e) cudaEventDestroy(e);
+        for (cudaEvent_t e : {b, g2, a, l3, l4}) if (e) cudaEventDestroy(e);
     }
 };
 }  // namespace
@@ -445,6 +449,8 @@ static int prove_impl(zk_ctx *ctx, const zk_params *p, size_t batch,
     ZK_TRY(ctx->g_scal3.reserve(batch * nA * 32));
     if (!ctx->aux2) { ZK_TRY(zk_ctx_create(ctx->device, nullptr, &ctx->aux2)); ctx->aux2->opts = ctx->opts; }    // third lane for the A and B1 MSMs
     zk_ctx *lane3 = ctx->aux2;
+    if (!ctx->aux3) { ZK_TRY(zk_ctx_create(ctx->device, nullptr, &ctx->aux3)); ctx->aux3->opts = ctx->opts; }    // fourth lane for the B1 MSM
+    zk_ctx *lane4 = ctx->aux3;
     auto rnd = [](size_t b) { return (b + 255) & ~(size_t)255; };
     size_t misc_bytes = rnd(a_idx.size() * 4 + 4) + rnd(bi_idx.size() * 4 + 4) + rnd(ba_idx.size() * 4 + 4) + 2 * rnd(batch * 32) + rnd(batch * 128) +
                         4 * rnd(batch * sizeof(G1XYZZ)) + rnd(2 * batch * sizeof(G1XYZZ)) + rnd(batch * sizeof(G2XYZZ)) + rnd(batch * 192);
@@ -474,9 +480,9 @@ static int prove_impl(zk_ctx *ctx, const zk_params *p, size_t batch,
     if (ba_idx.size()) k_gather32<<<dim3((unsigned)((ba_idx.size() + 255) / 256), (unsigned)batch), 256, 0, st>>>(d_aux, n_aux, d_baidx, ba_idx.size(), scal2, nB, bi_idx.size());
     k_put_terms<<<(unsigned)((batch + 63) / 64), 64, 0, st>>>((const uint4 *)d_terms, 0, 2, 2, scal2, nB, nB - 2, batch);
     LaneEvents ev;
-    ev.lane2 = lane2; ev.lane3 = lane3;
+    ev.lane2 = lane2; ev.lane3 = lane3; ev.lane4 = lane4;
     ZK_TRY(ev.create());
-    cudaEvent_t ev_b = ev.b, ev_g2 = ev.g2, ev_a = ev.a, ev_l3 = ev.l3;
+    cudaEvent_t ev_b = ev.b, ev_g2 = ev.g2, ev_a = ev.a, ev_l3 = ev.l3, ev_l4 = ev.l4;
     ZK_CUDA(cudaEventRecord(ev_b, st));
     ZK_CUDA(cudaStreamWaitEvent(lane2->stream, ev_b, 0));
     ev.lanes_started = true;
@@ -490,13 +496,17 @@ static int prove_impl(zk_ctx *ctx, const zk_params *p, size_t batch,
     k_put_terms<<<(unsigned)((batch + 63) / 64), 64, 0, st>>>((const uint4 *)d_terms, 0, 1, 2, scal3, nA, nA - 2, batch);
     ZK_CUDA(cudaEventRecord(ev_a, st));
     ZK_CUDA(cudaStreamWaitEvent(lane3->stream, ev_a, 0));
+    ZK_CUDA(cudaStreamWaitEvent(lane4->stream, ev_b, 0));              // the B scalars (scal2) are complete at ev_b
+    // lane 3: g_a, then s * g_a; lane 4: g_b1, then r * g_b1 — each variable-base multiplication needs only its own lane's MSM, and
+    // both run under the NTT -> H -> L chain of the first lane
     ZK_TRY(zk_msm_run(lane3, p->a, scal3, nA, batch));
     ZK_CUDA(cudaMemcpyAsync(d_ga, lane3->result.p, batch * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, lane3->stream));
-    ZK_TRY(zk_msm_run(lane3, p->b1, scal2, nB, batch));
-    ZK_CUDA(cudaMemcpyAsync(d_gb1, lane3->result.p, batch * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, lane3->stream));
-    // s*g_a and r*g_b1 need only this lane's results, so they run here, under the NTT -> H -> L chain of the first lane
-    k_scale_points<<<(unsigned)(2 * batch), SCALE_T, 0, lane3->stream>>>(d_ga, d_gb1, (const uint32_t *)d_terms, batch, d_T);
+    k_scale_points<<<(unsigned)batch, SCALE_T, 0, lane3->stream>>>(d_ga, d_gb1, (const uint32_t *)d_terms, batch, 0, d_T);
     ZK_CUDA(cudaEventRecord(ev_l3, lane3->stream));
+    ZK_TRY(zk_msm_run(lane4, p->b1, scal2, nB, batch));
+    ZK_CUDA(cudaMemcpyAsync(d_gb1, lane4->result.p, batch * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, lane4->stream));
+    k_scale_points<<<(unsigned)batch, SCALE_T, 0, lane4->stream>>>(d_ga, d_gb1, (const uint32_t *)d_terms, batch, 1, d_T);
+    ZK_CUDA(cudaEventRecord(ev_l4, lane4->stream));
     if (r1cs) {
         ZK_TRY(ctx->g_b.reserve(batch * (n_in + n_aux) * 32));       // z in Montgomery form
         ZK_TRY(zk_fr_witness_to_mont(ctx, d_in, n_in, d_aux, n_aux, batch, ctx->g_b.p));
@@ -523,18 +533,19 @@ static int prove_impl(zk_ctx *ctx, const zk_params *p, size_t batch,
     // L
     ZK_TRY(zk_msm_run(ctx, p->l, d_aux, n_aux, batch));
     ZK_CUDA(cudaMemcpyAsync(d_L, ctx->result.p, batch * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, st));
-    ZK_CUDA(cudaStreamWaitEvent(st, ev_l3, 0));                       // join: g_a, g_b1 and the scaled points T from the third lane
+    ZK_CUDA(cudaStreamWaitEvent(st, ev_l3, 0));                       // join: g_a and s * g_a from the third lane
+    ZK_CUDA(cudaStreamWaitEvent(st, ev_l4, 0));                       // join: r * g_b1 from the fourth
     ZK_CUDA(cudaStreamWaitEvent(st, ev_g2, 0));                       // join: g_b (G2) is ready in d_gb
     // ---- assembly + Proof::write ----
-    k_finish_proofs<<<(unsigned)((batch + 63) / 64), 64, 0, st>>>(d_ga, d_gb, d_T, d_H, d_L, batch, d_proofs);
+    k_finish_proofs<<<(unsigned)((batch + 31) / 32), 96, 0, st>>>(d_ga, d_gb, d_T, d_H, d_L, batch, d_proofs);
     ZK_CUDA(cudaGetLastError());
     ZK_CUDA(cudaMemcpyAsync(proofs_out, d_proofs, batch * 192, cudaMemcpyDeviceToHost, st));
     int rc = zk_check_err_flag(ctx);    // synchronises this lane (which has joined the second); reports non-canonical scalars
     std::string msg = rc ? zk_last_error() : "";
-    int rcb = zk_check_err_flag(lane2), rcc = zk_check_err_flag(lane3);
+    int rcb = zk_check_err_flag(lane2), rcc = zk_check_err_flag(lane3), rcd = zk_check_err_flag(lane4);
     if (rc) zk_set_error("%s", msg.c_str());
     ev.completed = true;                // every lane has been synchronised and its error flag read
-    return rc ? rc : (rcb ? rcb : rcc);
+    return rc ? rc : (rcb ? rcb : (rcc ? rcc : rcd));
 }
 
 extern "C" int zk_groth16_prove_batch(zk_ctx *ctx, const zk_params *p, size_t batch,

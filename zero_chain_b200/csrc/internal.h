@@ -73,7 +73,8 @@ struct zk_ctx {
     // live kernel timing (zk_ctx_profile): CUDA events around the dominant kernel on ctx->stream
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_events;   // pairs (start, stop)
-    zk_ctx *aux2 = nullptr;        // third lane: the A and B1 MSMs (independent of the NTT chain)
+    zk_ctx *aux2 = nullptr;        // third lane: the A MSM and s * g_a (independent of the NTT chain)
+    zk_ctx *aux3 = nullptr;        // fourth lane: the B1 MSM and r * g_b1
     DevBuf g_scal3;                // A-query scalars
     zk_ctx *aux = nullptr;         // second lane (own stream + workspace) on the same device: the prover's G2 MSM overlaps the G1 work
     DevBuf g_scal2;                // B-query scalars (shared by the G1 and G2 B MSMs)
