@@ -115,9 +115,9 @@ int zk_fr_into_repr(zk_ctx *ctx, const void *d_h, unsigned log_m, size_t n_out, 
 int zk_fr_blinding_terms(zk_ctx *ctx, const void *d_r, const void *d_s, size_t batch, void *d_out);
 int zk_check_err_flag(zk_ctx *ctx);
 // lane-parallel verifier kernels (pairing_lanes.cu)
-void zk_launch_miller_lanes(cudaStream_t st, int minb, size_t n, const void *a, const void *acc, const void *c, const void *coef_b, const void *gamma, int gamma_inf,
+void zk_launch_miller_lanes(cudaStream_t st, size_t n, const void *a, const void *acc, const void *c, const void *coef_b, const void *gamma, int gamma_inf,
                             const void *delta, int delta_inf, const uint8_t *status, void *f);
-void zk_launch_verify_final_lanes(cudaStream_t st, int minb, size_t n, const void *f, const void *alpha_beta, const uint8_t *status, uint8_t *verdict);
+void zk_launch_verify_final_lanes(cudaStream_t st, size_t n, const void *f, const void *alpha_beta, const uint8_t *status, uint8_t *verdict);
 int zk_fr_to_mont(zk_ctx *ctx, const void *d_in, size_t n, void *d_out);
 int zk_fr_witness_to_mont(zk_ctx *ctx, const void *d_inputs, size_t n_in, const void *d_aux, size_t n_aux, size_t batch, void *d_z);
 int zk_fr_r1cs_eval(zk_ctx *ctx, const uint32_t *d_row_ptr, const uint32_t *d_col, const void *d_coeff, const void *d_z, size_t n_c, size_t n_in,

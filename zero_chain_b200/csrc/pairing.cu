@@ -359,9 +359,8 @@ extern "C" int zk_groth16_verify_batch_device(zk_ctx *ctx, const zk_pvk *k, size
     k_g2_prepare<<<grid(n), PT, 0, st>>>(b, n, 0, coef, 1, n, stt + 1, 3);
     ZK_CUDA(cudaStreamWaitEvent(st, ev.e[1], 0)); ZK_CUDA(cudaStreamWaitEvent(st, ev.e[2], 0));
     if (ctx->opts.verify_lanes) {       // six lanes per proof: one merged Miller loop, then the final exponentiation (pairing_lanes.cu)
-        const int minb = ctx->opts.verify_lanes == 3 ? 3 : 2;       // resident blocks per SM (register budget 168 / 255) of the lane kernels
-        zk_launch_miller_lanes(st, minb, n, a, acc, c, coef, k->gamma, k->gamma_inf, k->delta, k->delta_inf, stt, f);
-        zk_launch_verify_final_lanes(st, minb, n, f, k->alpha_beta, stt, d_verdicts);
+        zk_launch_miller_lanes(st, n, a, acc, c, coef, k->gamma, k->gamma_inf, k->delta, k->delta_inf, stt, f);
+        zk_launch_verify_final_lanes(st, n, f, k->alpha_beta, stt, d_verdicts);
     } else {
         k_miller<<<grid(3 * n), PT, 0, st>>>(n, a, acc, c, coef, k->gamma, k->gamma_inf, k->delta, k->delta_inf, stt, f);
         k_verify_final<<<grid(n), PT, 0, st>>>(n, f, k->alpha_beta, stt, d_verdicts);

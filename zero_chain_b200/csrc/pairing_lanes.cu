@@ -9,8 +9,8 @@ typedef Affine<Fq> G1A;
 constexpr uint8_t zkcodec_DEC_INFINITY = 6;      // zkcodec::DEC_INFINITY (codec.cuh; not included here to keep this unit small)
 
 // one group of six lanes per proof: f[i] = conj of the product of the three Miller loops (A_i, B_i), (acc_i, -gamma), (C_i, -delta)
-template <int MINB>
-static __global__ void __launch_bounds__(128, MINB) k_miller_lanes(size_t n, const G1A *__restrict__ a, const G1A *__restrict__ acc, const G1A *__restrict__ c,
+// 255 registers (2 CTAs / SM): a 168-register build spilled inside the Fq2 product and measured slower (profiles/r02_experiments.md §3)
+static __global__ void __launch_bounds__(128, 2) k_miller_lanes(size_t n, const G1A *__restrict__ a, const G1A *__restrict__ acc, const G1A *__restrict__ c,
                                                                 const zkpair::LineCoeff *__restrict__ coef_b, const zkpair::LineCoeff *__restrict__ gamma, int gamma_inf,
                                                                 const zkpair::LineCoeff *__restrict__ delta, int delta_inf, const uint8_t *__restrict__ st,
                                                                 zkpair::Fq12 *__restrict__ f) {
@@ -36,8 +36,7 @@ static __global__ void __launch_bounds__(128, MINB) k_miller_lanes(size_t n, con
     if (in_range && L.live && !rejected) reinterpret_cast<Fq2 *>(f + i)[slot_index(L.t)] = r;
 }
 // verdict: 1 = Ok(true), 0 = Ok(false), 2 = Proof::read -> InvalidData, 3 = Proof::read -> PointInfinity (first failing point)
-template <int MINB>
-static __global__ void __launch_bounds__(128, MINB) k_verify_final_lanes(size_t n, const zkpair::Fq12 *__restrict__ f, const zkpair::Fq12 *__restrict__ alpha_beta,
+static __global__ void __launch_bounds__(128, 2) k_verify_final_lanes(size_t n, const zkpair::Fq12 *__restrict__ f, const zkpair::Fq12 *__restrict__ alpha_beta,
                                                                       const uint8_t *__restrict__ st, uint8_t *__restrict__ verdict) {
     const Lane L = Lane::make();
     const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -54,17 +53,15 @@ static __global__ void __launch_bounds__(128, MINB) k_verify_final_lanes(size_t 
     if (in_range && L.live && L.t == 0) verdict[i] = bad ? bad : ((eq && !zero) ? 1 : 0);
 }
 
-void zk_launch_miller_lanes(cudaStream_t st, int minb, size_t n, const void *a, const void *acc, const void *c, const void *coef_b, const void *gamma, int gamma_inf,
+void zk_launch_miller_lanes(cudaStream_t st, size_t n, const void *a, const void *acc, const void *c, const void *coef_b, const void *gamma, int gamma_inf,
                             const void *delta, int delta_inf, const uint8_t *status, void *f) {
     const size_t warps = (n + GROUPS_PER_WARP - 1) / GROUPS_PER_WARP;
     const unsigned g = (unsigned)((warps * 32 + 127) / 128);
-    (void)minb;
-    k_miller_lanes<2><<<g, 128, 0, st>>>(n, (const G1A *)a, (const G1A *)acc, (const G1A *)c, (const zkpair::LineCoeff *)coef_b, (const zkpair::LineCoeff *)gamma, gamma_inf,
+    k_miller_lanes<<<g, 128, 0, st>>>(n, (const G1A *)a, (const G1A *)acc, (const G1A *)c, (const zkpair::LineCoeff *)coef_b, (const zkpair::LineCoeff *)gamma, gamma_inf,
                                              (const zkpair::LineCoeff *)delta, delta_inf, status, (zkpair::Fq12 *)f);
 }
-void zk_launch_verify_final_lanes(cudaStream_t st, int minb, size_t n, const void *f, const void *alpha_beta, const uint8_t *status, uint8_t *verdict) {
+void zk_launch_verify_final_lanes(cudaStream_t st, size_t n, const void *f, const void *alpha_beta, const uint8_t *status, uint8_t *verdict) {
     const size_t warps = (n + GROUPS_PER_WARP - 1) / GROUPS_PER_WARP;
     const unsigned g = (unsigned)((warps * 32 + 127) / 128);
-    (void)minb;
-    k_verify_final_lanes<2><<<g, 128, 0, st>>>(n, (const zkpair::Fq12 *)f, (const zkpair::Fq12 *)alpha_beta, status, verdict);
+    k_verify_final_lanes<<<g, 128, 0, st>>>(n, (const zkpair::Fq12 *)f, (const zkpair::Fq12 *)alpha_beta, status, verdict);
 }
