@@ -36,3 +36,26 @@ for n in [int(x) for x in sys.argv[1:]] or [1024, 4096, 8192, 16384, 32768, 6553
     ms = e0.elapsed_time(e1) / 2
     assert bool((dv == 1).all())
     print("n=%6d  %8.2f ms  %9.0f verifications/s" % (n, ms, n / ms * 1e3), flush=True)
+
+# two contexts, half a batch each, enqueued back to back (both calls are asynchronous on their context's stream)
+ctx_b = zk.Context(0)
+pvk_b = pvk          # the prepared key is read-only and shareable between contexts of one device
+for n in [int(x) for x in sys.argv[1:]] or [8192]:
+    h = n // 2
+    dp = torch.from_numpy(np.tile(proof, n)).cuda()
+    di = torch.from_numpy(np.tile(inp, n).view(np.int64)).cuda()
+    dv = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    def both():
+        zk._ck(_lib.lib().zk_groth16_verify_batch_device(ctx._h, pvk._h, h, C.c_void_p(dp.data_ptr()), C.c_void_p(di.data_ptr()), 22, C.c_void_p(dv.data_ptr())))
+        zk._ck(_lib.lib().zk_groth16_verify_batch_device(ctx_b._h, pvk._h, n - h, C.c_void_p(dp.data_ptr() + 192 * h), C.c_void_p(di.data_ptr() + 32 * 22 * h), 22, C.c_void_p(dv.data_ptr() + h)))
+    from zero_chain_b200 import _lib
+    import ctypes as C
+    both(); ctx.sync(); ctx_b.sync()
+    t = time.perf_counter()
+    for _ in range(3):
+        both()
+    ctx.sync(); ctx_b.sync()
+    ms = (time.perf_counter() - t) / 3 * 1e3
+    assert bool((dv == 1).all())
+    print("two contexts: n=%6d  %8.2f ms  %9.0f verifications/s" % (n, ms, n / ms * 1e3), flush=True)
