@@ -118,6 +118,12 @@ def test_verify_batch_matches_oracle(ctx):
     want = [int(pr.verify_prepared(ab, gam, dlt, vk["ic"], pr.proof_read(p), x)) for p, x in zip(all_p, all_i)]
     assert want == [1, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0]
     assert got == want
+    # the thread-per-proof kernels (kept as the A/B reference of the lane-parallel ones) give the same verdicts
+    ctx.set_opt(zk.Context.OPT_VERIFY_LANES, 0)
+    try:
+        assert zk.verify_proofs(pvk, b"".join(all_p), all_i) == want
+    finally:
+        ctx.set_opt(zk.Context.OPT_VERIFY_LANES, 1)
     assert zk.verify_proof(pvk, proofs[0], inputs[0]) is True
     # the same key loaded from its PreparedVerifyingKey::write image gives the same verdicts
     k2 = zk.PreparedVerifyingKey.read(ctx, pvk.write())
