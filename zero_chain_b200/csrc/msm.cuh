@@ -444,6 +444,10 @@ __global__ void __launch_bounds__(RED_T) k_finish_bits(const XYZZ<F> *__restrict
 // tail idx >= S-1 stays at the all-zero infinity pattern written by a memset), so ONE per-bit reduction over 2*n_dom
 // pseudo-domains of NR points finishes both weighted sums.
 // GL lanes per item: 8 for many domains (work-bound), 32 inside a warp.
+// one out-of-line copy of the full addition for k_rowcol_sums: inlined at its three call sites the kernel was ~21 000 instructions and
+// spent more cycles waiting for instructions than issuing them (ncu: stall no_instruction 5.6 per issue, fmaheavy 44 %)
+template <class F>
+__device__ __noinline__ void add_outline(XYZZ<F> &acc, const XYZZ<F> &o) { acc.add(o); }
 template <class F, int GL>
 __global__ void __launch_bounds__(RED_T, (sizeof(F) == sizeof(Fq) ? ZK_RC_MINB : 1)) k_rowcol_sums(const XYZZ<F> *__restrict__ B, int N, int s, int n_dom, XYZZ<F> *__restrict__ rc) {
     extern __shared__ unsigned char smraw[];
@@ -460,16 +464,16 @@ __global__ void __launch_bounds__(RED_T, (sizeof(F) == sizeof(Fq) ? ZK_RC_MINB :
         const XYZZ<F> *p = B + (size_t)dom * N;
         if (idx < nr) {
             int hi = idx + 1;
-            for (int lo = sub; lo < S; lo += GL) { int d = hi * S + lo; if (d <= N) acc.add(p[d - 1]); }
+            for (int lo = sub; lo < S; lo += GL) { int d = hi * S + lo; if (d <= N) add_outline(acc, p[d - 1]); }
         } else {
             int lo = idx - nr + 1;
-            for (int hi = sub; hi <= nr; hi += GL) { int d = hi * S + lo; if (d <= N) acc.add(p[d - 1]); }
+            for (int hi = sub; hi <= nr; hi += GL) { int d = hi * S + lo; if (d <= N) add_outline(acc, p[d - 1]); }
         }
     }
     slot[lane] = acc;
     __syncwarp();
     for (int o = GL / 2; o > 0; o >>= 1) {
-        if (sub < (uint32_t)o) { XYZZ<F> x = slot[lane]; x.add(slot[lane + o]); slot[lane] = x; }
+        if (sub < (uint32_t)o) { XYZZ<F> x = slot[lane]; add_outline(x, slot[lane + o]); slot[lane] = x; }
         __syncwarp();
     }
     if (live && sub == 0) {
