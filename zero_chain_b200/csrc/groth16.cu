@@ -28,6 +28,7 @@ struct zk_params {
     // resident CRS: G1 = alpha_g1, beta_g1, delta_g1, ic[n_ic]; G2 = beta_g2, gamma_g2, delta_g2 (affine, Montgomery)
     G1Affine *d_vk1 = nullptr;
     G2Affine *d_vk2 = nullptr;
+    bool subgroup_checked = false;     // every point passed the r-torsion test at load time (checked load, or a cache written by one)
 };
 
 // The fixed constraint system of one circuit, resident on the device in CSR form.
@@ -152,7 +153,9 @@ extern "C" int zk_params_load(zk_ctx *ctx, const uint8_t *buf, size_t len, int c
     ZK_TRY(params_walk(buf, len, voff, vcnt));
     CrsLayout L(vcnt);
     ZK_TRY(params_decode(ctx, buf, len, checked, voff, L));
-    return params_from_device(ctx, L, ctx->stage_b.as<G1Affine>(), ctx->stage_c.as<G2Affine>(), out);
+    ZK_TRY(params_from_device(ctx, L, ctx->stage_b.as<G1Affine>(), ctx->stage_c.as<G2Affine>(), out));
+    (*out)->subgroup_checked = checked != 0;
+    return ZK_OK;
 }
 
 // ---- Parameters::write from the resident CRS --------------------------------------------------------------------------
@@ -283,7 +286,9 @@ extern "C" int zk_params_load_cached(zk_ctx *ctx, const uint8_t *buf, size_t len
             ZK_CUDA(cudaMemcpyAsync(ctx->stage_c.p, body.data() + b1, b2, cudaMemcpyHostToDevice, ctx->stream));
             ZK_CUDA(cudaStreamSynchronize(ctx->stream));
             if (cache_hit) *cache_hit = 1;
-            return params_from_device(ctx, L, ctx->stage_b.as<G1Affine>(), ctx->stage_c.as<G2Affine>(), out);
+            ZK_TRY(params_from_device(ctx, L, ctx->stage_b.as<G1Affine>(), ctx->stage_c.as<G2Affine>(), out));
+            (*out)->subgroup_checked = true;       // the cache is only ever written after a checked load, and its body is hash-guarded
+            return ZK_OK;
         }
     }
     // miss (absent, other key, truncated): the full checked load, then the cache is (re)written
@@ -293,6 +298,7 @@ extern "C" int zk_params_load_cached(zk_ctx *ctx, const uint8_t *buf, size_t len
     ZK_CUDA(cudaMemcpyAsync(body.data() + b1, ctx->stage_c.p, b2, cudaMemcpyDeviceToHost, ctx->stream));
     ZK_CUDA(cudaStreamSynchronize(ctx->stream));
     ZK_TRY(params_from_device(ctx, L, ctx->stage_b.as<G1Affine>(), ctx->stage_c.as<G2Affine>(), out));
+    (*out)->subgroup_checked = true;
     { Sha256 sh; sh.update(body.data(), body.size()); sh.finish(want.body_sha); }
     std::string tmp = std::string(cache_path) + ".tmp";
     if (FILE *f = fopen(tmp.c_str(), "wb")) {           // a cache that cannot be written is not an error of the load
@@ -330,24 +336,58 @@ __global__ void k_put_terms(const uint4 *__restrict__ terms, int sel0, int sel1,
 // dependent point operations; here thread 0 runs the doubling chain 2^i P into shared memory (the only serial part) and the
 // block then sums the selected powers: 4 per thread, then a 6-level tree — about 2.5x less latency for the same group element.
 constexpr int SCALE_T = 64;
+// `glv` != 0 (the CRS was loaded CHECKED, so g_a and g_b1 lie in the r-torsion): k P is split with the curve endomorphism
+// phi(x, y) = (beta x, y) = -[u^2] P (u the BLS parameter; the identity the subgroup test of codec.cuh uses, exact on G1):
+// k = k1 u^2 + k0 by plain division (k0, k1 < 2^128), so k P = k0 P - k1 phi(P) and phi(2^i P) = 2^i phi(P): the doubling chain
+// is 127 steps instead of 254.  Without the guarantee (unchecked load) the plain 254-step chain is used: same group element either way.
 __global__ void __launch_bounds__(SCALE_T) k_scale_points(const G1XYZZ *__restrict__ ga, const G1XYZZ *__restrict__ gb1, const uint32_t *__restrict__ terms,
-                                                          size_t batch, int j, G1XYZZ *__restrict__ T) {
+                                                          size_t batch, int j, int glv, G1XYZZ *__restrict__ T) {
     __shared__ G1XYZZ pw[255];                                                   // 2^i P, i <= 254; reused for the tree (47.8 KB)
+    __shared__ uint32_t kk[2][4];                                                // glv: k0, k1
     const size_t b = blockIdx.x, id = 2 * b + j;                                 // one launch per product kind j (each on the lane that made its point)
     const int t = threadIdx.x;
     const uint32_t *k = terms + (b * 4 + (j ? 1 : 2)) * 8;                       // j=0: s, j=1: r
     int top = -1;
     for (int i = 7; i >= 0 && top < 0; i--) if (k[i]) top = 32 * i + 31 - __clz(k[i]);
     if (top > 254) top = 254;          // a non-canonical r / s (>= 2^255) is reported through the error flag by k_blinding_terms; stay inside pw[]
+    if (glv && top > 127) top = 127;   // quotient and remainder are below 2^128 (u^2 > 2^127, k < 2^255)
     if (t < 32) {                                                               // warp 0: the doubling chain, three cooperative stages per doubling
         G1XYZZ d = j ? gb1[b] : ga[b];
         if (t == 0) pw[0] = d;
         for (int i = 1; i <= top; i++) { zkcoop::dbl(d); if (t == 0) pw[i] = d; }
+    } else if (glv && t == 32) {                                                // meanwhile, on the other warp: k = k1 * u^2 + k0 by shift-and-subtract
+        const uint32_t dv[4] = {0x00000000u, 0x00000001u, 0x0001a402u, 0xac45a401u};        // u^2 = 0xd201000000010000^2
+        uint32_t rem[5] = {0, 0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+        for (int i = 254; i >= 0; i--) {
+            for (int w = 4; w > 0; w--) rem[w] = (rem[w] << 1) | (rem[w - 1] >> 31);
+            rem[0] = (rem[0] << 1) | ((k[i >> 5] >> (i & 31)) & 1);
+            bool ge = rem[4] != 0;
+            if (!ge) { ge = true; for (int w = 3; w >= 0; w--) { if (rem[w] != dv[w]) { ge = rem[w] > dv[w]; break; } } }
+            if (ge) {
+                uint64_t br = 0;
+                for (int w = 0; w < 4; w++) { uint64_t x = (uint64_t)rem[w] - dv[w] - br; rem[w] = (uint32_t)x; br = (x >> 63) & 1; }
+                rem[4] -= (uint32_t)br;
+                if (i < 128) q[i >> 5] |= 1u << (i & 31);
+            }
+        }
+        for (int w = 0; w < 4; w++) { kk[0][w] = rem[w]; kk[1][w] = q[w]; }
     }
     __syncthreads();
     G1XYZZ acc = G1XYZZ::inf();
-    for (int i = 4 * t; i < 4 * t + 4 && i <= top; i++)
-        if ((k[i >> 5] >> (i & 31)) & 1) acc.add(pw[i]);
+    if (!glv) {
+        for (int i = 4 * t; i < 4 * t + 4 && i <= top; i++)
+            if ((k[i >> 5] >> (i & 31)) & 1) acc.add(pw[i]);
+    } else {                                                                    // threads 0..31: bits of k0 on 2^i P; 32..63: bits of k1 on -phi(2^i P)
+        const int half = t >> 5, i0 = 4 * (t & 31);
+        const uint32_t beta_w[12] = ZK_ENDO_BETA_INIT;
+        Fq beta; for (int w = 0; w < 12; w++) beta.l[w] = beta_w[w];
+        for (int i = i0; i < i0 + 4 && i <= top; i++)
+            if ((kk[half][i >> 5] >> (i & 31)) & 1) {
+                G1XYZZ p = pw[i];
+                if (half) { p.x = p.x * beta; p.y = p.y.neg(); }
+                acc.add(p);
+            }
+    }
     __syncthreads();                                                             // every thread is done reading the powers
     G1XYZZ *part = pw;
     part[t] = acc;
@@ -497,16 +537,6 @@ static int prove_impl(zk_ctx *ctx, const zk_params *p, size_t batch,
     ZK_CUDA(cudaEventRecord(ev_a, st));
     ZK_CUDA(cudaStreamWaitEvent(lane3->stream, ev_a, 0));
     ZK_CUDA(cudaStreamWaitEvent(lane4->stream, ev_b, 0));              // the B scalars (scal2) are complete at ev_b
-    // lane 3: g_a, then s * g_a; lane 4: g_b1, then r * g_b1 — each variable-base multiplication needs only its own lane's MSM, and
-    // both run under the NTT -> H -> L chain of the first lane
-    ZK_TRY(zk_msm_run(lane3, p->a, scal3, nA, batch));
-    ZK_CUDA(cudaMemcpyAsync(d_ga, lane3->result.p, batch * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, lane3->stream));
-    k_scale_points<<<(unsigned)batch, SCALE_T, 0, lane3->stream>>>(d_ga, d_gb1, (const uint32_t *)d_terms, batch, 0, d_T);
-    ZK_CUDA(cudaEventRecord(ev_l3, lane3->stream));
-    ZK_TRY(zk_msm_run(lane4, p->b1, scal2, nB, batch));
-    ZK_CUDA(cudaMemcpyAsync(d_gb1, lane4->result.p, batch * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, lane4->stream));
-    k_scale_points<<<(unsigned)batch, SCALE_T, 0, lane4->stream>>>(d_ga, d_gb1, (const uint32_t *)d_terms, batch, 1, d_T);
-    ZK_CUDA(cudaEventRecord(ev_l4, lane4->stream));
     if (r1cs) {
         ZK_TRY(ctx->g_b.reserve(batch * (n_in + n_aux) * 32));       // z in Montgomery form
         ZK_TRY(zk_fr_witness_to_mont(ctx, d_in, n_in, d_aux, n_aux, batch, ctx->g_b.p));
@@ -529,6 +559,19 @@ static int prove_impl(zk_ctx *ctx, const zk_params *p, size_t batch,
     k_put_terms<<<(unsigned)((batch + 63) / 64), 64, 0, st>>>((const uint4 *)d_terms, 3, 3, 1, scal, nH, m - 1, batch);
     ZK_TRY(zk_msm_run(ctx, p->h, scal, nH, batch));
     ZK_CUDA(cudaMemcpyAsync(d_H, ctx->result.p, batch * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, st));
+    // (the host enqueues the LONGEST chains first — G2 above, NTTs -> H here — and only then the two shorter lanes below: with ~130 launches
+    //  per proof the order in which they reach the streams is worth ~0.3 ms of single-proof latency)
+    // lane 3: g_a, then s * g_a; lane 4: g_b1, then r * g_b1 — each variable-base multiplication needs only its own lane's MSM, and
+    // both run under the NTT -> H -> L chain of the first lane
+    ZK_TRY(zk_msm_run(lane3, p->a, scal3, nA, batch));
+    ZK_CUDA(cudaMemcpyAsync(d_ga, lane3->result.p, batch * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, lane3->stream));
+    const int glv = p->subgroup_checked ? 1 : 0;
+    k_scale_points<<<(unsigned)batch, SCALE_T, 0, lane3->stream>>>(d_ga, d_gb1, (const uint32_t *)d_terms, batch, 0, glv, d_T);
+    ZK_CUDA(cudaEventRecord(ev_l3, lane3->stream));
+    ZK_TRY(zk_msm_run(lane4, p->b1, scal2, nB, batch));
+    ZK_CUDA(cudaMemcpyAsync(d_gb1, lane4->result.p, batch * sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, lane4->stream));
+    k_scale_points<<<(unsigned)batch, SCALE_T, 0, lane4->stream>>>(d_ga, d_gb1, (const uint32_t *)d_terms, batch, 1, glv, d_T);
+    ZK_CUDA(cudaEventRecord(ev_l4, lane4->stream));
     // ---- assignments (already on the device: d_in, d_aux) ----
     // L
     ZK_TRY(zk_msm_run(ctx, p->l, d_aux, n_aux, batch));

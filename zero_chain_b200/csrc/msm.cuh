@@ -408,29 +408,30 @@ __global__ void __launch_bounds__(RED_T) k_sum_points(const XYZZ<F> *__restrict_
     warp_tree(slot, acc, lane);
     if (lane == 0) out[g] = acc;
 }
-// one WARP per domain: R = sum_b 2^b X_b as a binary tree — at level s lane i (i % 2^(s+1) == 0) computes
-// X_i += 2^(2^s) * X_(i+2^s).  Serial depth 15 doublings + 4 additions instead of 15 + 15 for a Horner chain.
+// one BLOCK per domain: R = sum_b 2^b X_b as a binary tree — at level s the pair (i, i + 2^s), i % 2^(s+1) == 0, becomes
+// X_i += 2^(2^s) * X_(i+2^s).  Serial depth 15 doublings + 4 additions (n_bits <= 16) instead of 15 + 15 for a Horner chain, and every
+// pair of a level has its own WARP running the doublings / the addition cooperatively (curve_coop.cuh: 3 / 4 dependent stages instead
+// of 9 / 14 products), which is what matters here: the kernel is pure latency (one domain for a single MSM).
+constexpr int FIN_WARPS = 10;          // pairs of the first level: n_bits <= 20
 template <class F>
-__global__ void __launch_bounds__(RED_T) k_finish_bits(const XYZZ<F> *__restrict__ X, int n_bits, int n_dom, XYZZ<F> *__restrict__ R) {
+__global__ void __launch_bounds__(FIN_WARPS * 32) k_finish_bits(const XYZZ<F> *__restrict__ X, int n_bits, int n_dom, XYZZ<F> *__restrict__ R) {
     extern __shared__ unsigned char smraw[];
-    uint32_t lane = threadIdx.x & 31;
-    XYZZ<F> *slot = reinterpret_cast<XYZZ<F> *>(smraw) + (threadIdx.x >> 5) * 32;
-    int dom = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    XYZZ<F> *vals = reinterpret_cast<XYZZ<F> *>(smraw);          // 2 * FIN_WARPS points
+    const int dom = blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (dom >= n_dom) return;
-    XYZZ<F> v = (int)lane < n_bits ? X[(size_t)dom * n_bits + lane] : XYZZ<F>::inf();
-    slot[lane] = v;
-    __syncwarp();
+    if (threadIdx.x < 2 * FIN_WARPS) vals[threadIdx.x] = (int)threadIdx.x < n_bits ? X[(size_t)dom * n_bits + threadIdx.x] : XYZZ<F>::inf();
+    __syncthreads();
     for (int s = 0; (1 << s) < n_bits; s++) {
-        int step = 1 << s;
-        if ((lane & (2 * step - 1)) == 0 && (int)lane + step < n_bits) {
-            XYZZ<F> hi = slot[lane + step];
-            for (int k = 0; k < step; k++) hi = hi.dbl();
-            v.add(hi);
-            slot[lane] = v;
+        const int step = 1 << s, i = w * 2 * step;
+        if (i + step < n_bits) {                                 // warp-uniform
+            XYZZ<F> hi = vals[i + step], v = vals[i];
+            for (int k = 0; k < step; k++) zkcoop::dbl(hi);
+            zkcoop::add(v, hi);
+            if (lane == 0) vals[i] = v;
         }
-        __syncwarp();
+        __syncthreads();
     }
-    if (lane == 0) R[dom] = v;
+    if (threadIdx.x == 0) R[dom] = vals[0];
 }
 // ---- two-level bucket reduction for many domains (batched proving) -----------------------------------------
 // sum_d d*B[d] with d = hi*S + lo (S = 2^s):  S * sum_hi hi*R_hi + sum_lo lo*C_lo,  R_hi / C_lo = row / column sums

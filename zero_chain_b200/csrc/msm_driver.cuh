@@ -214,7 +214,7 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
         size_t n_w = (size_t)slices * bits * nd, n_g = nd * (size_t)bits;
         k_bit_sums<F><<<(unsigned)((n_w * 32 + RED_T - 1) / RED_T), RED_T, sm_warp, st>>>(Bk, N, slices, bits, (int)nd, part);
         k_sum_points<F><<<(unsigned)((n_g * 32 + RED_T - 1) / RED_T), RED_T, sm_warp, st>>>(part, slices, (int)n_g, X);
-        k_finish_bits<F><<<(unsigned)((nd * 32 + RED_T - 1) / RED_T), RED_T, sm_warp, st>>>(X, bits, (int)nd, out);
+        k_finish_bits<F><<<(unsigned)nd, FIN_WARPS * 32, 2 * FIN_WARPS * sizeof(XYZZ<F>), st>>>(X, bits, (int)nd, out);
     };
     XYZZ<F> *Rdom = tables ? R : R + 1;      // per-domain results; without tables they are the window sums the Horner pass folds into R[0]
     if ((n_dom >= 8 && c >= 7) || (tables && c > 16)) {
