@@ -380,8 +380,9 @@ def gather_ints(dist, torch, world, value):
     if world == 1:
         return [value]
     limbs = np.array([(value >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(4)], dtype=np.uint64)
-    t = torch.from_numpy(limbs.view(np.int64)).cuda()
-    out = torch.zeros(4 * world, dtype=torch.int64, device="cuda")
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"       # gloo in the CPU test of this plumbing
+    t = torch.from_numpy(limbs.view(np.int64)).to(dev)
+    out = torch.zeros(4 * world, dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(out, t)
     rows = out.cpu().numpy().view(np.uint64).reshape(world, 4)
     return [sum(int(x) << (64 * j) for j, x in enumerate(r)) for r in rows]
