@@ -529,7 +529,8 @@ static int prove_impl(zk_ctx *ctx, const zk_params *p, size_t batch,
     ZK_TRY(zk_msm_run(lane2, p->b2, scal2, nB, batch));
     ZK_CUDA(cudaMemcpyAsync(d_gb, lane2->result.p, batch * sizeof(G2XYZZ), cudaMemcpyDeviceToDevice, lane2->stream));
     ZK_CUDA(cudaEventRecord(ev_g2, lane2->stream));
-    // third lane: g_a = MSM(a', inputs ++ aux|A ++ [1, r]) and g_b1 = MSM(b_g1', B scalars) need only the assignment too
+    // third / fourth lane: g_a = MSM(a', inputs ++ aux|A ++ [1, r]) and g_b1 = MSM(b_g1', B scalars) need only the assignment too: their
+    // scalars are built and the events recorded here, the MSMs themselves are enqueued after the longer chains (below)
     uint4 *scal3 = ctx->g_scal3.as<uint4>();
     ZK_CUDA(cudaMemcpy2DAsync(scal3, nA * 32, d_in, n_in * 32, n_in * 32, batch, cudaMemcpyDeviceToDevice, st));
     if (a_idx.size()) k_gather32<<<dim3((unsigned)((a_idx.size() + 255) / 256), (unsigned)batch), 256, 0, st>>>(d_aux, n_aux, d_aidx, a_idx.size(), scal3, nA, n_in);
