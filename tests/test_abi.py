@@ -61,3 +61,17 @@ def test_hot_kernel_sass_uses_fused_wide_multiplies():
         assert len(fn) == 1, (key, names)
         sass = subprocess.check_output(["cuobjdump", "-sass", "-fun", fn[0], _lib.SO_PATH], stderr=subprocess.STDOUT).decode()
         assert sass.count("IMAD.WIDE.U32") > 500 and "STL" not in sass and "LDL" not in sass, key
+
+
+def test_lane_verifier_kernels_keep_fq12_out_of_local_memory():
+    """The lane-parallel Miller loop must not spill its Fq12 state (round 1's thread-per-proof kernels carried 1 301 / 4 285 LDL/STL
+    instructions and 18 GB of local-memory write-back per 32 k proofs)."""
+    from zero_chain_b200 import _lib
+    names = subprocess.check_output("cuobjdump -sass %s | grep 'Function :'" % _lib.SO_PATH, shell=True).decode()
+    for key, limit in (("k_miller_lanes", 100), ("k_verify_final_lanes", 1000)):
+        fn = [l.split(":")[1].strip() for l in names.splitlines() if key in l]
+        assert len(fn) == 1, (key, names)
+        sass = subprocess.check_output(["cuobjdump", "-sass", "-fun", fn[0], _lib.SO_PATH], stderr=subprocess.STDOUT).decode()
+        body = [l for l in sass.splitlines() if "/*" in l and ("LDL" in l or "STL" in l)]
+        n = len(set(l.split("*/")[0] for l in body))          # one line per instruction address (the listing repeats encodings)
+        assert n < limit, (key, n)
