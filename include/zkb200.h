@@ -144,7 +144,9 @@ int zk_params_write_vk(zk_ctx *ctx, const zk_params *p, uint8_t *out);
  * core/proofs/src/crypto_components.rs:320-328).  If `cache_path` holds the decoded Montgomery points of exactly these bytes
  * (SHA-256 of the whole stream, length and vector counts are compared, and the cached points carry their own SHA-256), they are uploaded as they are — no decoding, no on-curve
  * or subgroup tests (*cache_hit = 1).  Otherwise the stream goes through the full CHECKED load and the cache file is (re)written
- * atomically (*cache_hit = 0); a cache that cannot be written is not an error.  cache_hit may be NULL. */
+ * atomically (*cache_hit = 0); a cache that cannot be written is not an error.  cache_hit may be NULL.
+ * Trust: the hashes guard against corruption and against a cache of another key, not against an adversary who can write
+ * `cache_path` (they could store off-curve points with a matching body hash) — keep the file where the proving key itself lives. */
 int zk_params_load_cached(zk_ctx *ctx, const uint8_t *pk_bytes, size_t len, const char *cache_path, int *cache_hit, zk_params **out);
 
 /* create_proof for ONE already-synthesised witness (the Rust shim runs ProvingAssignment::synthesize

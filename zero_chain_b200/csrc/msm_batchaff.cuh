@@ -231,7 +231,7 @@ template <class F, bool FIRST, int MINB>
 __global__ void __launch_bounds__(BA_T, MINB) k_ba_backward(const Affine<F> *__restrict__ in_pts, const uint32_t *__restrict__ off_out, uint32_t n_buckets, int K,
                                                              const F *__restrict__ prefix, const uint2 *__restrict__ srcs, const F *__restrict__ block_inv,
                                                              Affine<F> *__restrict__ out_pts) {
-    constexpr int PV = (int)(sizeof(Affine<F>) / 16), FV = (int)(sizeof(F) / 16), SLOT = 2 * PV + FV;     // two points + one prefix element
+    constexpr int PV = (int)(sizeof(Affine<F>) / 16), FV = (int)(sizeof(F) / 16);     // a slot = two points + one prefix element
     extern __shared__ unsigned char ba_smem[];
     uint4 *stage = reinterpret_cast<uint4 *>(ba_smem);
     const uint32_t total = off_out[n_buckets];

@@ -93,10 +93,15 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
     //     rounds cheaper, not wrong).
     const Affine<F> *cur_pts = (const Affine<F> *)b->d_tbl;
     const uint32_t *cur_sorted = ctx->sorted.as<uint32_t>(), *cur_off = ctx->bucket_off.as<uint32_t>(), *cur_sizes = ctx->sizes.as<uint32_t>();
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;      // zk_ctx_profile: the bucket-accumulation stage (affine rounds, if any, + the XYZZ pass)
+    // zk_ctx_profile: the bucket-accumulation stage (affine rounds, if any, + the XYZZ pass); destroyed here unless handed to the context
+    struct ProfPair {
+        cudaEvent_t a = nullptr, b = nullptr; bool kept = false;
+        ~ProfPair() { if (!kept) { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); } }
+    } prof;
+    cudaEvent_t &ev0 = prof.a, &ev1 = prof.b;
     {
         int levels = 0;
-        if (ctx->opts.ba_min_entries >= 0 && (long)E >= ctx->opts.ba_min_entries) {      // a round costs ~0.1 ms of latency (its inversion): small MSMs stay on the XYZZ pass alone
+        if (ctx->opts.ba_min_entries >= 0 && (long)E >= ctx->opts.ba_min_entries) {      // small MSMs stay on the XYZZ pass alone (see above)
             if (ctx->opts.ba_levels >= 0) levels = (int)(ctx->opts.ba_levels < BA_MAX_LEVELS ? ctx->opts.ba_levels : BA_MAX_LEVELS);
             else for (size_t avg = E / NB; avg >= 12 && levels < BA_MAX_LEVELS; avg >>= 1) levels++;      // 26 per bucket -> 2 rounds, 76 -> 3 (measured)
         }
@@ -189,7 +194,7 @@ int msm_run_t(zk_ctx *ctx, const zk_bases *b, const uint32_t *d_scalars, size_t 
         if (ctx->prof_on && !ev0) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, st); }
         k_accumulate<F, 3><<<grid, 128, 0, st>>>(tb, so, bo, to, (uint32_t)NB, order, partials);      // 3 CTAs / SM (168 registers): measured best of 2 / 3 / 4
     }
-    if (ctx->prof_on) { cudaEventRecord(ev1, st); ctx->prof_events.push_back(ev0); ctx->prof_events.push_back(ev1); }
+    if (ctx->prof_on) { cudaEventRecord(ev1, st); ctx->prof_events.push_back(ev0); ctx->prof_events.push_back(ev1); prof.kept = true; }
     if (ctx->split_tail) {             // asynchronous MSM: combine / reduction continue on the high-priority tail stream
         ZK_CUDA(cudaEventRecord(ctx->ev_front, st));
         ZK_CUDA(cudaStreamWaitEvent(ctx->tail, ctx->ev_front, 0));
