@@ -427,6 +427,7 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) k_finish_bits(const XYZZ<F> *_
             XYZZ<F> hi = vals[i + step], v = vals[i];
             for (int k = 0; k < step; k++) zkcoop::dbl(hi);
             zkcoop::add(v, hi);
+            __syncwarp();                                        // every lane has read vals[i] before lane 0 overwrites it
             if (lane == 0) vals[i] = v;
         }
         __syncthreads();
