@@ -54,6 +54,8 @@ static void run(int lanes, Fn fn) {
 }
 }  // namespace simt
 static inline uint32_t __shfl_sync(unsigned, uint32_t v, int src) { return simt::exchange(v, src); }
+static inline uint32_t __shfl_up_sync(unsigned, uint32_t v, int delta) { const int l = threadIdx.x & 31; return simt::exchange(v, l - delta >= 0 ? l - delta : l); }
+static inline uint32_t __shfl_down_sync(unsigned, uint32_t v, int delta) { const int l = threadIdx.x & 31; return simt::exchange(v, l + delta < simt::n_lanes ? l + delta : l); }
 static inline unsigned __ballot_sync(unsigned, bool v) {
     unsigned m = 0;
     for (int l = 0; l < simt::n_lanes; l++) m |= (simt::exchange(v ? 1u : 0u, l) & 1u) << l;
@@ -62,6 +64,7 @@ static inline unsigned __ballot_sync(unsigned, bool v) {
 
 #include "pairing_lanes.cuh"
 #include "curve_coop.cuh"
+#include "msm_warp_scan.cuh"
 using namespace zkpair;
 using namespace zklanes;
 
@@ -164,3 +167,14 @@ static int t_coop(int op, int lanes, const uint32_t *pa, const uint32_t *pb, uin
 }
 extern "C" int emu_coop_g1(int op, int lanes, const uint32_t *a, const uint32_t *b, uint32_t *o) { return t_coop<Fq>(op, lanes, a, b, o); }
 extern "C" int emu_coop_g2(int op, int lanes, const uint32_t *a, const uint32_t *b, uint32_t *o) { return t_coop<Fq2>(op, lanes, a, b, o); }
+
+// ---- warp products of the batched-affine rounds (msm_warp_scan.cuh) ---------------------------------------------------------
+// totals: 32 field elements (one per lane); others[l] = product of the other 31, all[l] = product of all 32 (every lane)
+template <class F>
+static void t_warp_products(const uint32_t *totals, uint32_t *others, uint32_t *all) {
+    const F *T = reinterpret_cast<const F *>(totals);
+    F *O = reinterpret_cast<F *>(others), *A = reinterpret_cast<F *>(all);
+    simt::run(32, [&](int lane) { zkmsm::ba_warp_products(T[lane], O[lane], A[lane]); });
+}
+extern "C" void emu_warp_products_fq(const uint32_t *t, uint32_t *o, uint32_t *a) { t_warp_products<Fq>(t, o, a); }
+extern "C" void emu_warp_products_fq2(const uint32_t *t, uint32_t *o, uint32_t *a) { t_warp_products<Fq2>(t, o, a); }

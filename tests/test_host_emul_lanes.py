@@ -13,7 +13,7 @@ import pytest
 
 from oracle import coracle as co
 from oracle import pyref as pr
-from tests.test_host_emul_pairing import Q, _p, arr_f12, f12_arr, g1_arr, g2_arr, rand_f12
+from tests.test_host_emul_pairing import Q, _p, arr_f12, f12_arr, fq_words, g1_arr, g2_arr, rand_f12, words_fq
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
@@ -146,3 +146,37 @@ def test_cooperative_point_operations(emu, g):
                 for op, want in ((0, dbl(a2)), (1, add(a2, b3)), (2, dbl(a2)), (3, inf), (4, b3), (5, a2)):
                     assert fn(op, lanes, _p(np.ascontiguousarray(a)), _p(np.ascontiguousarray(b)), _p(o)) == 0, (op, lanes)
                     assert np.array_equal(o, want), (op, lanes)
+
+
+def test_warp_products_of_the_batched_affine_rounds(emu):
+    """msm_warp_scan.cuh ba_warp_products on 32 lanes: `others` = the product of the other 31 thread totals (prefix x suffix of two
+    Kogge-Stone scans), `all` = the warp total in every lane — what lets ONE inversion per round serve every thread."""
+    rng = pr.SplitMix64(909)
+    for case in range(3):
+        t = [rng.below(Q, 7) or 1 for _ in range(32)]
+        if case == 1:
+            t[0] = 1; t[31] = Q - 1; t[7] = 1                              # ones at the ends (threads without a division)
+        if case == 2:
+            t = [1] * 32; t[13] = 5
+        T = np.array([w for v in t for w in fq_words(v)], dtype=np.uint32)
+        O, A = np.zeros_like(T), np.zeros_like(T)
+        emu.emu_warp_products_fq(_p(T), _p(O), _p(A))
+        total = 1
+        for v in t:
+            total = total * v % Q
+        for l in range(32):
+            assert words_fq(A[12 * l:12 * l + 12]) == total
+            assert words_fq(O[12 * l:12 * l + 12]) == total * pow(t[l], -1, Q) % Q
+    # Fq2 totals (the G2 rounds)
+    t2 = [(rng.below(Q, 7), rng.below(Q, 7)) for _ in range(32)]
+    T = np.array([w for v in t2 for c in v for w in fq_words(c)], dtype=np.uint32)
+    O, A = np.zeros_like(T), np.zeros_like(T)
+    emu.emu_warp_products_fq2(_p(T), _p(O), _p(A))
+    F = pr.FQ2
+    total = (1, 0)
+    for v in t2:
+        total = F.mul(total, v)
+    for l in range(32):
+        got_all = (words_fq(A[24 * l:24 * l + 12]), words_fq(A[24 * l + 12:24 * l + 24]))
+        got_oth = (words_fq(O[24 * l:24 * l + 12]), words_fq(O[24 * l + 12:24 * l + 24]))
+        assert got_all == total and F.mul(got_oth, t2[l]) == total
